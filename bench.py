@@ -1,0 +1,395 @@
+#!/usr/bin/env python3
+"""bench.py -- PageRank edges/s on synthetic RMAT (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--scale S] [--impl b200|reference]
+
+A "step" is one complete hot-path pass: ParallelIterativePageRank semantics with
+(max_iterations=20, damping=0.85, stop_epsilon=0.0) over the device-resident graph, i.e. 20 power
+iterations + the final normalise (SURVEY 8d timed region; graph generation, CSR build and ingest are
+reported separately).  value = E * iterations * steps / device time (CUDA events on the launching
+stream, max over ranks).  e2e = the same metric through the public C-ABI call with a HOST output
+buffer (params from host memory in, double[N] ranks copied device->host inside the timed region).
+
+--impl reference times the reference's own algorithm (oracle/_ref, compiled from
+/root/reference by oracle/Makefile; the plain-C port in oracle/ when that is absent) on the box's
+host cores, all threads, on a bounded sample of the same workload (RMAT of a smaller scale).
+
+N > 1: launched by torchrun, one rank per GPU; every rank builds its vertex partition of the same
+RMAT graph and the partitions exchange contributions over NVLink peer memory inside the kernels
+(torch.distributed is used only to swap IPC handles and to take the max of the timings).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+ITERATIONS = 20
+DAMPING = 0.85
+EDGE_FACTOR = 16
+SEED = 42
+ALGO_BYTES_PER_EDGE = 12  # 4 B column index + 8 B gathered FP64 contribution      
+ALGO_BYTES_PER_ROW = 24   # 4 B row offset + 4 B out-degree + 8 B old + 8 B new rank
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---- clocks sampling (nvidia-smi during the timed region) ---------------------------------------------
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- peaks ----------------------------------------------------------------------------------------------
+
+def hbm_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        v = float(json.load(open(p))["hbm_gbs"])
+        return v, "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture (or None)."""
+    try:
+        return json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return None
+
+
+# ---- reference arm / cpu baseline -------------------------------------------------------------------------
+
+def cpu_reference_run(scale, steps, warmup, threads=None):
+    """Times the reference's ParallelIterativePageRank (only that call, like the GPU side) on an RMAT
+    graph of `scale`.  Returns dict(value, kind, cores, sample, ms_per_step, build_s)."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from _checkers import Oracle, Reference  # noqa: E402  (bench.py's reference leg may execute oracle/)
+    import memgraph_b200 as mg
+    threads = threads or os.cpu_count() or 1
+    n, m = 1 << scale, EDGE_FACTOR << scale
+    s, t = mg.rmat_edges_host(scale, m, seed=SEED)
+    t0 = time.perf_counter()
+    if Reference.available():
+        impl, kind = Reference(), "reference"
+        g = impl.graph(n, s, t)
+        run = lambda: impl.run(g, n, max_iterations=ITERATIONS, damping_factor=DAMPING, stop_epsilon=0.0,
+                               num_of_threads=threads)
+    else:
+        impl, kind = Oracle(), "port"
+        g = impl.graph(n, s, t)
+        threads = 1  # the C port walks the blocks sequentially
+        run = lambda: impl.run(g, n, max_iterations=ITERATIONS, damping_factor=DAMPING, stop_epsilon=0.0,
+                               num_of_threads=1)
+    build_s = time.perf_counter() - t0
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = time.perf_counter() - t0
+    impl.free(g)
+    return {"value": m * ITERATIONS * steps / dt, "unit": "edges/s", "cores": threads, "kind": kind,
+            "sample": f"RMAT scale-{scale} EF{EDGE_FACTOR} (N={n}, E={m}), {ITERATIONS} iterations, stop_epsilon=0, "
+                      f"{steps} timed call(s) of ParallelIterativePageRank; graph ctor {build_s:.1f}s excluded",
+            "ms_per_step": dt / steps * 1e3, "build_s": build_s}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    res = cpu_reference_run(args.cpu_scale, max(1, args.steps), max(0, args.warmup))
+    line = {
+        "impl": "reference", "metric": "pagerank_edges_per_second", "value": res["value"], "unit": "edges/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"PageRank RMAT scale-{args.scale} EF16, 20 iterations, d=0.85, stop_epsilon=0 "
+                               f"(reference arm: bounded sample = RMAT scale-{args.cpu_scale})"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---- B200 arm ------------------------------------------------------------------------------------------------
+
+def dev_alloc(N, lib, device, nbytes):
+    p = N.vp()
+    rc = lib.mgb200_device_malloc(device, nbytes, ctypes.byref(p))
+    if rc:
+        raise RuntimeError(lib.mgb200_last_error().decode())
+    return p
+
+
+def run_b200_arm(args):
+    import memgraph_b200 as mg
+    from memgraph_b200 import _native as N
+    from memgraph_b200.pagerank import make_params, _check, _stats
+    lib = N.lib()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            log(f"bench.py: --gpus {args.gpus} needs torchrun (WORLD_SIZE={world}); running rank 0 only is invalid")
+            return 2
+    device = local_rank
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+
+    scale = args.scale
+    n, m = 1 << scale, EDGE_FACTOR << scale
+    t0 = time.perf_counter()
+    d_from = dev_alloc(N, lib, device, 4 * m)
+    d_to = dev_alloc(N, lib, device, 4 * m)
+    mg.rmat_edges_device(scale, m, d_from, d_to, seed=SEED, device=device)
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    g = mg.PageRankGraph.from_device(n, m, d_from, d_to, device=device, part_rank=rank, part_world=world)
+    build_wall_s = time.perf_counter() - t0
+    lib.mgb200_device_free(device, d_from)
+    lib.mgb200_device_free(device, d_to)
+    info = g.info
+    log(f"[rank {rank}] RMAT scale-{scale}: gen {gen_s:.2f}s, build {build_wall_s:.2f}s (device {info['build_ms']:.0f} ms), "
+        f"rows {info['local_rows']} edges {info['local_edges']} heavy_rows {info['heavy_rows']} "
+        f"heavy_edges {info['heavy_edges']} segs {info['heavy_segments']} sell_rows {info['sell_rows']} "
+        f"sell_entries {info['sell_entries']} zero_rows {info['zero_rows']} resident {info['resident_bytes']/2**30:.2f} GiB")
+
+    if world > 1:
+        import torch
+        handle = ctypes.create_string_buffer(N.IPC_HANDLE_BYTES)
+        _check(lib.mgb200_graph_export_window(g.handle, handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, handle.raw)
+        arr = (N.vp * world)()
+        keep = []
+        for q in range(world):
+            if q != rank:
+                buf = ctypes.create_string_buffer(handles[q], N.IPC_HANDLE_BYTES)
+                keep.append(buf)
+                arr[q] = ctypes.cast(buf, N.vp)
+        _check(lib.mgb200_graph_connect_peers(g.handle, arr, None))
+        dist.barrier()
+
+    local_rows = info["local_rows"]
+    d_out = dev_alloc(N, lib, device, 8 * max(n if world == 1 else local_rows, 1))
+
+    def step_device(timed_kernel=False):
+        p, _cb = make_params(ITERATIONS, DAMPING, 0.0, on_device=True, time_spmv_kernel=timed_kernel)
+        st = N.RunStatsC()
+        if world == 1:
+            _check(lib.mgb200_pagerank_run(g.handle, ctypes.byref(p), d_out, ctypes.byref(st)))
+        else:
+            _check(lib.mgb200_pagerank_run_partition(g.handle, ctypes.byref(p), d_out, None, ctypes.byref(st)))
+        return _stats(st)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(device)
+    if rank == 0:
+        sampler.start()
+    step_ms, launches, kernel_ms, kernel_launches, iters = [], 0, 0.0, 0, 0
+    for _ in range(args.steps):
+        if dist is not None:
+            dist.barrier()
+        st = step_device(timed_kernel=True)
+        step_ms.append(st.iterate_ms)
+        launches += st.kernel_launches
+        kernel_ms += st.kernel_ms
+        kernel_launches += st.kernel_timed_launches
+        iters = st.iterations
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = float(sum(step_ms))
+    if dist is not None:
+        import torch
+        tm = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{device}")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        total_ms = float(tm.item())
+        ln = torch.tensor([launches], dtype=torch.int64, device=f"cuda:{device}")
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln.item())
+    assert iters == ITERATIONS, f"executed {iters} iterations, expected {ITERATIONS}"
+    value = m * ITERATIONS * args.steps / (total_ms * 1e-3)
+
+    # e2e: the public call with a HOST output buffer (D2H of the ranks inside the timed region)
+    e2e = None
+    if world == 1:
+        pinned = None
+        try:
+            import torch  # plumbing: pinned host memory for the output buffer
+            pinned = torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
+        except Exception as ex:  # pragma: no cover
+            log("pinned allocation failed, using pageable host memory:", ex)
+        host_out = pinned if pinned is not None else np.empty(n, dtype=np.float64)
+        g.run(ITERATIONS, DAMPING, 0.0, out=host_out)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            _, st = g.run(ITERATIONS, DAMPING, 0.0, out=host_out)
+        e2e_dt = time.perf_counter() - t0
+        e2e = {"value": m * ITERATIONS * args.steps / e2e_dt, "unit": "edges/s",
+               "h2d_bytes_per_step": ctypes.sizeof(N.RunParams), "d2h_bytes_per_step": 8 * n,
+               "api": "mgb200_pagerank_run(graph, params, host_rank_out) == ParallelIterativePageRank(graph, ...) -> "
+                      "std::vector<double>", "rank_sum_check": float(host_out[:n].sum())}
+    else:
+        # partitioned: each rank copies its slice of the ranks to host memory inside the timed call
+        host_out = np.empty(max(local_rows, 1), dtype=np.float64)
+        host_vtx = np.empty(max(local_rows, 1), dtype=np.uint32)
+        p, _cb = make_params(ITERATIONS, DAMPING, 0.0)
+        st = N.RunStatsC()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            _check(lib.mgb200_pagerank_run_partition(g.handle, ctypes.byref(p), host_out.ctypes.data,
+                                                     host_vtx.ctypes.data, ctypes.byref(st)))
+        import torch
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{device}")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        sm = torch.tensor([float(host_out[:local_rows].sum())], dtype=torch.float64, device=f"cuda:{device}")
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        e2e = {"value": m * ITERATIONS * args.steps / float(dt.item()), "unit": "edges/s",
+               "h2d_bytes_per_step": ctypes.sizeof(N.RunParams) * world, "d2h_bytes_per_step": 12 * n,
+               "api": "mgb200_pagerank_run_partition(graph, params, host_rank_out, host_vertex_out) on every rank",
+               "rank_sum_check": float(sm.item())}
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = hbm_peak()
+    sell_edges = info["local_edges"] - info["heavy_edges"]
+    roofline = None
+    if kernel_launches:
+        per_launch_bytes = ALGO_BYTES_PER_EDGE * sell_edges + ALGO_BYTES_PER_ROW * info["sell_rows"]
+        avg_ms = kernel_ms / kernel_launches
+        achieved = per_launch_bytes / (avg_ms * 1e-3) / 1e9
+        traffic = ncu_traffic()
+        roofline = {"bound": "hbm", "kernel": "sell_rows_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "peak_source": peak_src,
+                    "traffic": (traffic or {}).get("sell_rows_kernel_dram_bytes_per_launch") if world == 1 else None,
+                    "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_ms,
+                    "timed_launches": kernel_launches,
+                    "units_per_launch": {"edges": sell_edges, "rows": info["sell_rows"]},
+                    "whole_iteration": {
+                        "algorithmic_bytes": ALGO_BYTES_PER_EDGE * m + ALGO_BYTES_PER_ROW * n,
+                        "achieved": (ALGO_BYTES_PER_EDGE * m + ALGO_BYTES_PER_ROW * n) * ITERATIONS * args.steps
+                        / (total_ms * 1e-3) / 1e9 / world,
+                        "frac": (ALGO_BYTES_PER_EDGE * m + ALGO_BYTES_PER_ROW * n) * ITERATIONS * args.steps
+                        / (total_ms * 1e-3) / 1e9 / world / peak,
+                        "note": "12E+24N per iteration over the whole timed region (all kernels, per GPU)"}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_reference_run(args.cpu_scale, 1, 0)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:
+            log("cpu_baseline failed:", ex)
+
+    line = {
+        "metric": "pagerank_edges_per_second", "value": value, "unit": "edges/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"PageRank RMAT scale-{scale} EF16 (N={n}, E={m}), {ITERATIONS} iterations, d={DAMPING}, "
+                               f"stop_epsilon=0, seed {SEED}", "parallelism": f"vertex-partition x{world}",
+                   "l2": "inputs larger than L2 (index stream %.1f GB/iteration)" % (4 * m / 1e9),
+                   "graph_gen_s": gen_s, "graph_build_ms": info["build_ms"],
+                   "heavy_rows": info["heavy_rows"], "heavy_edges": info["heavy_edges"], "sell_rows": info["sell_rows"],
+                   "sell_entries": info["sell_entries"], "zero_rows": info["zero_rows"]},
+        "ms_per_iteration": total_ms / args.steps / ITERATIONS,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=int, default=int(os.environ.get("MGB200_BENCH_SCALE", "26")))
+    ap.add_argument("--cpu-scale", type=int, default=int(os.environ.get("MGB200_CPU_SCALE", "22")),
+                    help="RMAT scale of the bounded CPU sample (reference arm / cpu_baseline)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

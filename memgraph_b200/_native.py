@@ -1,0 +1,75 @@
+"""ctypes binding of include/mgb200_pagerank.h.  Fails loudly when the library is missing: the
+product has no fallback (build with `python -m memgraph_b200.build` or __graft_entry__.build())."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libmgb200_pagerank.so")
+
+u64, u32, f64, i32 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_double, ctypes.c_int
+vp = ctypes.c_void_p
+
+OK, ERR_INVALID_ARGUMENT, ERR_ZERO_THREADS, ERR_CUDA, ERR_ABORTED, ERR_COMM = 0, 1, 2, 3, 4, 5
+IPC_HANDLE_BYTES = 64
+
+
+class GraphInfo(ctypes.Structure):
+    _fields_ = [("node_count", u64), ("edge_count", u64), ("part_rank", u32), ("part_world", u32),
+                ("local_rows", u64), ("local_edges", u64), ("heavy_rows", u64), ("heavy_edges", u64),
+                ("heavy_segments", u64), ("sell_rows", u64), ("sell_slices", u64), ("sell_entries", u64),
+                ("zero_rows", u64), ("resident_bytes", u64), ("build_ms", f64)]
+
+
+class RunStatsC(ctypes.Structure):
+    _fields_ = [("iterations", u64), ("last_diff", f64), ("rank_sum", f64), ("iterate_ms", f64), ("kernel_ms", f64),
+                ("kernel_timed_launches", u64), ("kernel_launches", u64), ("spmv_launches", u64)]
+
+
+ABORT_FN = ctypes.CFUNCTYPE(ctypes.c_int, vp)
+
+
+class RunParams(ctypes.Structure):
+    _fields_ = [("max_iterations", u64), ("damping_factor", f64), ("stop_epsilon", f64), ("should_abort", ABORT_FN),
+                ("abort_user", vp), ("rank_out_on_device", i32), ("time_spmv_kernel", i32)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes) -- one entry per function declared in include/mgb200_pagerank.h
+    "mgb200_last_error": (ctypes.c_char_p, []),
+    "mgb200_device_count": (i32, [ctypes.POINTER(i32)]),
+    "mgb200_graph_create_host": (i32, [i32, u64, u64, vp, vp, u32, u32, ctypes.POINTER(vp)]),
+    "mgb200_graph_create_device": (i32, [i32, u64, u64, vp, vp, u32, u32, ctypes.POINTER(vp)]),
+    "mgb200_graph_destroy": (None, [vp]),
+    "mgb200_graph_get_info": (i32, [vp, ctypes.POINTER(GraphInfo)]),
+    "mgb200_pagerank_run": (i32, [vp, ctypes.POINTER(RunParams), vp, ctypes.POINTER(RunStatsC)]),
+    "mgb200_parallel_iterative_pagerank": (i32, [u64, u64, vp, vp, u64, f64, f64, u32, vp, ctypes.POINTER(u64)]),
+    "mgb200_graph_export_window": (i32, [vp, vp]),
+    "mgb200_graph_connect_peers": (i32, [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]),
+    "mgb200_pagerank_run_partition": (i32, [vp, ctypes.POINTER(RunParams), vp, vp, ctypes.POINTER(RunStatsC)]),
+    "mgb200_rmat_generate_device": (i32, [i32, u32, u64, u64, u64, f64, f64, f64, vp, vp]),
+    "mgb200_rmat_generate_host": (i32, [u32, u64, u64, u64, f64, f64, f64, vp, vp]),
+    "mgb200_device_malloc": (i32, [i32, ctypes.c_size_t, ctypes.POINTER(vp)]),
+    "mgb200_device_free": (i32, [i32, vp]),
+    "mgb200_copy_to_device": (i32, [i32, vp, vp, ctypes.c_size_t]),
+    "mgb200_copy_to_host": (i32, [i32, vp, vp, ctypes.c_size_t]),
+    "mgb200_device_info": (i32, [i32, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(i32),
+                                 ctypes.POINTER(ctypes.c_size_t)]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA extension is required (no CPU fallback). "
+                "Build it with `python -m memgraph_b200.build`.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export what the header declares
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib

@@ -1,0 +1,111 @@
+"""In-tree build of the native artefacts (nvcc cross-compiles sm_100a without a GPU).
+
+    memgraph_b200/_build/libmgb200_pagerank.so   C ABI of include/mgb200_pagerank.h (CUDA runtime linked statically)
+    memgraph_b200/_build/pagerank.so             drop-in Memgraph query module (mgp_init_module / mgp_shutdown_module)
+    memgraph_b200/_build/libmgp_fake_host.so     fake mgp host used by the tests to load query modules without Memgraph
+
+Objects are rebuilt only when a source or header is newer.  `python -m memgraph_b200.build` builds everything.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+OUT = os.path.join(PKG, "_build")
+INCLUDE = os.path.join(REPO, "include")
+
+NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+CXX = os.environ.get("CXX") or shutil.which("g++") or "g++"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "-Xptxas", "-v",
+    "-I", INCLUDE, "-I", CSRC,
+    "-diag-suppress", "1444",  # cub::TransformInputIterator deprecation notice
+]
+CUDA_SOURCES = ["pagerank_kernels.cu", "graph_build.cu", "capi.cu"]
+HEADERS = [os.path.join(CSRC, "core.hpp"), os.path.join(CSRC, "rmat.hpp"), os.path.join(INCLUDE, "mgb200_pagerank.h"),
+           os.path.join(INCLUDE, "mgp_abi.h")]
+
+CORE_LIB = os.path.join(OUT, "libmgb200_pagerank.so")
+MODULE_LIB = os.path.join(OUT, "pagerank.so")
+FAKE_HOST_LIB = os.path.join(OUT, "libmgp_fake_host.so")
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd, log_name=None):
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if log_name:
+        with open(os.path.join(OUT, log_name), "w") as f:
+            f.write(" ".join(cmd) + "\n" + proc.stdout)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout)
+        raise RuntimeError("build step failed: " + " ".join(cmd))
+    return proc.stdout
+
+
+def build_core(verbose=False):
+    os.makedirs(OUT, exist_ok=True)
+    objs = []
+    for src in CUDA_SOURCES:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(OUT, src.replace(".cu", ".o"))
+        if _newer(obj, [path] + HEADERS):
+            if verbose:
+                print("nvcc", src, flush=True)
+            _run([NVCC] + NVCC_FLAGS + ["-c", path, "-o", obj], log_name=src + ".ptxas.log")
+        objs.append(obj)
+    if _newer(CORE_LIB, objs):
+        # -fvisibility=hidden + explicit default visibility on the extern "C" API keeps the export list tight
+        _run([NVCC, "-shared", "-cudart", "static", "-o", CORE_LIB] + objs + ["-Xlinker", "--no-undefined"])
+    return objs
+
+
+def build_module(objs, verbose=False):
+    """The drop-in query module: module glue + the same CUDA objects, CUDA runtime static, so that
+    dlopen(RTLD_NOW | RTLD_LOCAL) needs nothing but the host's mgp_* symbols (module.cpp:861)."""
+    src = os.path.join(CSRC, "pagerank_module.cpp")
+    obj = os.path.join(OUT, "pagerank_module.o")
+    if _newer(obj, [src] + HEADERS):
+        if verbose:
+            print("g++ pagerank_module.cpp", flush=True)
+        _run([CXX, "-std=c++20", "-O2", "-fPIC", "-fvisibility=hidden", "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj])
+    if _newer(MODULE_LIB, objs + [obj]):
+        _run([NVCC, "-shared", "-cudart", "static", "-o", MODULE_LIB, obj] + objs)
+
+
+def build_fake_host(verbose=False):
+    src = os.path.join(CSRC, "mgp_fake_host.cpp")
+    if _newer(FAKE_HOST_LIB, [src] + HEADERS):
+        if verbose:
+            print("g++ mgp_fake_host.cpp", flush=True)
+        _run([CXX, "-std=c++20", "-O2", "-fPIC", "-shared", "-I", INCLUDE, "-o", FAKE_HOST_LIB, src, "-ldl"])
+
+
+def build_all(verbose=False):
+    objs = build_core(verbose)
+    if os.path.exists(os.path.join(CSRC, "pagerank_module.cpp")):
+        build_module(objs, verbose)
+    if os.path.exists(os.path.join(CSRC, "mgp_fake_host.cpp")):
+        build_fake_host(verbose)
+    out = {"core": CORE_LIB}
+    if os.path.exists(os.path.join(CSRC, "pagerank_module.cpp")):
+        out["module"] = MODULE_LIB
+    if os.path.exists(os.path.join(CSRC, "mgp_fake_host.cpp")):
+        out["fake_host"] = FAKE_HOST_LIB
+    return out
+
+
+if __name__ == "__main__":
+    print(build_all(verbose=True))

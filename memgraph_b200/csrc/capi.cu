@@ -1,0 +1,544 @@
+// memgraph_b200/csrc/capi.cu -- implementation of include/mgb200_pagerank.h (host orchestration).
+//
+// The host side only sequences work: ingest -> device build (graph_build.cu) -> batches of
+// iteration launches (pagerank_kernels.cu) with a device-side convergence flag, so the host
+// synchronises once per batch instead of once per iteration -> normalise -> copy out.
+// There is no CPU compute path: every entry point that needs a device fails with
+// MGB200_ERR_CUDA when none is usable.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "core.hpp"
+#include "rmat.hpp"
+
+struct mgb200_graph {
+  mgb200::Graph g;
+};
+
+namespace mgb200 {
+
+namespace {
+thread_local std::string tls_error;
+}
+
+void set_error(const std::string &msg) { tls_error = msg; }
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  char buf[512];
+  const char *base = strrchr(file, '/');
+  snprintf(buf, sizeof(buf), "CUDA error: %s (%s) at %s:%d [%s]", cudaGetErrorString(e), cudaGetErrorName(e),
+           base ? base + 1 : file, line, what);
+  set_error(buf);
+  cudaGetLastError();  // clear the sticky-less error so the next call reports its own
+  return MGB200_ERR_CUDA;
+}
+
+namespace {
+
+__global__ void rmat_kernel(uint32_t scale, uint64_t first_edge, uint64_t count, uint64_t seed, RmatThresholds t,
+                            uint32_t *from, uint32_t *to) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    uint32_t s, d;
+    rmat_edge(scale, first_edge + i, seed, t, s, d);
+    from[i] = s;
+    to[i] = d;
+  }
+}
+
+int check_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+  if (count <= 0) {
+    set_error("CUDA error: no CUDA device available (this library has no CPU fallback)");
+    return MGB200_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    set_error("invalid device ordinal " + std::to_string(device) + " (device count " + std::to_string(count) + ")");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  return MGB200_OK;
+}
+
+int validate_sizes(uint64_t n, uint32_t part_rank, uint32_t part_world) {
+  if (n >= 0xFFFFFFFFull) {
+    set_error("number_of_nodes must be < 2^32 - 1 (32-bit vertex labels)");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  if (part_world == 0 || part_world > static_cast<uint32_t>(kMaxPeers) || part_rank >= part_world) {
+    set_error("invalid partition: rank " + std::to_string(part_rank) + " of " + std::to_string(part_world));
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  return MGB200_OK;
+}
+
+// Iteration loop shared by the single- and multi-partition entry points.
+int iterate(Graph &g, const mgb200_run_params &p, mgb200_run_stats &stats) {
+  MGB_CUDA(cudaSetDevice(g.device));
+  IterateConfig cfg{p.max_iterations, p.damping_factor, p.stop_epsilon};
+  stats = mgb200_run_stats{};
+  if (g.n == 0) {
+    // The reference runs one pass over empty vectors when max_iterations != 0 (pagerank.cpp:201-231).
+    stats.iterations = p.max_iterations != 0 ? 1 : 0;
+    return MGB200_OK;
+  }
+  g.time_spmv = p.time_spmv_kernel != 0;
+  g.timed_launches = 0;
+  if (g.time_spmv && !g.kev[0])
+    for (auto &e : g.kev) MGB_CUDA(cudaEventCreate(&e));
+  int rc = launch_init(g);
+  if (rc) return rc;
+  rc = launch_barrier(g);  // peers have initialised before anyone pushes into their buffers
+  if (rc) return rc;
+  MGB_CUDA(cudaEventRecord(g.ev[2], g.stream));
+  uint64_t launches = 0, spmv = 0;
+  uint64_t it = 0;
+  bool done = p.max_iterations == 0;
+  const uint64_t batch_cap = 32;
+  while (!done) {
+    uint64_t batch = batch_cap;
+    if (p.max_iterations - it < batch) batch = p.max_iterations - it;
+    for (uint64_t b = 0; b < batch; ++b, ++it) {
+      rc = launch_iteration(g, it, cfg, &launches, &spmv);
+      if (rc) return rc;
+    }
+    MGB_CUDA(cudaMemcpyAsync(g.host_state, g.state, sizeof(IterState), cudaMemcpyDeviceToHost, g.stream));
+    MGB_CUDA(cudaStreamSynchronize(g.stream));
+    if (g.host_state->error) {
+      set_error("multi-GPU barrier timed out waiting for a peer partition");
+      return MGB200_ERR_COMM;
+    }
+    done = g.host_state->done != 0 || it >= p.max_iterations;
+    if (!done && p.should_abort && p.should_abort(p.abort_user)) {
+      set_error("aborted by the host (mgp_must_abort)");
+      return MGB200_ERR_ABORTED;
+    }
+  }
+  rc = launch_sum_and_exchange(g);
+  launches += 2;
+  if (rc) return rc;
+  MGB_CUDA(cudaEventRecord(g.ev[3], g.stream));
+  MGB_CUDA(cudaMemcpyAsync(g.host_state, g.state, sizeof(IterState), cudaMemcpyDeviceToHost, g.stream));
+  MGB_CUDA(cudaStreamSynchronize(g.stream));
+  if (g.host_state->error) {
+    set_error("multi-GPU barrier timed out waiting for a peer partition");
+    return MGB200_ERR_COMM;
+  }
+  float ms = 0.f;
+  MGB_CUDA(cudaEventElapsedTime(&ms, g.ev[2], g.ev[3]));
+  stats.iterations = g.host_state->iterations;
+  stats.last_diff = g.host_state->last_diff;
+  stats.rank_sum = g.host_state->rank_sum;
+  stats.iterate_ms = ms;
+  stats.kernel_launches = launches;
+  // launches past the convergence point return immediately; report the ones that did work
+  stats.spmv_launches = std::min<uint64_t>(spmv, stats.iterations);
+  const int timed = static_cast<int>(std::min<uint64_t>(g.timed_launches, stats.spmv_launches));
+  for (int i = 0; i < timed; ++i) {
+    float kms = 0.f;
+    MGB_CUDA(cudaEventElapsedTime(&kms, g.kev[2 * i], g.kev[2 * i + 1]));
+    stats.kernel_ms += kms;
+  }
+  stats.kernel_timed_launches = timed;
+  return MGB200_OK;
+}
+
+}  // namespace
+}  // namespace mgb200
+
+using namespace mgb200;
+
+extern "C" {
+
+const char *mgb200_last_error(void) { return tls_error.c_str(); }
+
+int mgb200_device_count(int *count_out) {
+  if (!count_out) return MGB200_ERR_INVALID_ARGUMENT;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) {
+    *count_out = 0;
+    return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+  }
+  *count_out = count;
+  return MGB200_OK;
+}
+
+int mgb200_graph_create_device(int device, uint64_t n, uint64_t m, const uint32_t *d_from, const uint32_t *d_to,
+                               uint32_t part_rank, uint32_t part_world, mgb200_graph **out) {
+  if (!out) return MGB200_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (m > 0 && (!d_from || !d_to)) {
+    set_error("null edge arrays");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  int rc = validate_sizes(n, part_rank, part_world);
+  if (rc) return rc;
+  rc = check_device(device);
+  if (rc) return rc;
+  auto *h = new (std::nothrow) mgb200_graph();
+  if (!h) {
+    set_error("out of host memory");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  h->g.device = device;
+  h->g.n = n;
+  h->g.m = m;
+  h->g.part_rank = part_rank;
+  h->g.part_world = part_world;
+  rc = build_graph(h->g, d_from, d_to);
+  if (rc) {
+    free_graph(h->g);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return MGB200_OK;
+}
+
+int mgb200_graph_create_host(int device, uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
+                             uint32_t part_rank, uint32_t part_world, mgb200_graph **out) {
+  if (!out) return MGB200_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (m > 0 && (!from || !to)) {
+    set_error("null edge arrays");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  int rc = validate_sizes(n, part_rank, part_world);
+  if (rc) return rc;
+  rc = check_device(device);
+  if (rc) return rc;
+  MGB_CUDA(cudaSetDevice(device));
+  // Stage the uint64 COO in chunks and narrow it to uint32 on the device.
+  uint32_t *d_from = nullptr, *d_to = nullptr;
+  uint64_t *d_stage = nullptr;
+  int *d_bad = nullptr;
+  const uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(m, 1), 1ull << 26);
+  auto cleanup = [&]() {
+    cudaFree(d_from);
+    cudaFree(d_to);
+    cudaFree(d_stage);
+    cudaFree(d_bad);
+  };
+  cudaError_t e;
+  if ((e = cudaMalloc(&d_from, std::max<uint64_t>(m, 1) * sizeof(uint32_t))) != cudaSuccess ||
+      (e = cudaMalloc(&d_to, std::max<uint64_t>(m, 1) * sizeof(uint32_t))) != cudaSuccess ||
+      (e = cudaMalloc(&d_stage, chunk * sizeof(uint64_t))) != cudaSuccess ||
+      (e = cudaMalloc(&d_bad, sizeof(int))) != cudaSuccess || (e = cudaMemset(d_bad, 0, sizeof(int))) != cudaSuccess) {
+    cleanup();
+    return cuda_fail(e, "cudaMalloc(COO staging)", __FILE__, __LINE__);
+  }
+  for (int side = 0; side < 2; ++side) {
+    const uint64_t *src = side == 0 ? from : to;
+    uint32_t *dst = side == 0 ? d_from : d_to;
+    for (uint64_t off = 0; off < m; off += chunk) {
+      const uint64_t cnt = std::min(chunk, m - off);
+      if ((e = cudaMemcpy(d_stage, src + off, cnt * sizeof(uint64_t), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cleanup();
+        return cuda_fail(e, "cudaMemcpy(COO H2D)", __FILE__, __LINE__);
+      }
+      rc = narrow_edges_u64_to_u32(device, nullptr, n, cnt, d_stage, dst + off, d_bad);
+      if (rc) {
+        cleanup();
+        return rc;
+      }
+    }
+  }
+  int bad = 0;
+  if ((e = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) {
+    cleanup();
+    return cuda_fail(e, "cudaMemcpy(flag)", __FILE__, __LINE__);
+  }
+  if (bad) {
+    cleanup();
+    set_error("edge endpoint out of range (>= number_of_nodes)");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  cudaFree(d_stage);
+  d_stage = nullptr;
+  rc = mgb200_graph_create_device(device, n, m, d_from, d_to, part_rank, part_world, out);
+  cleanup();
+  return rc;
+}
+
+void mgb200_graph_destroy(mgb200_graph *g) {
+  if (!g) return;
+  free_graph(g->g);
+  delete g;
+}
+
+int mgb200_graph_get_info(const mgb200_graph *h, mgb200_graph_info *info) {
+  if (!h || !info) return MGB200_ERR_INVALID_ARGUMENT;
+  const Graph &g = h->g;
+  info->node_count = g.n;
+  info->edge_count = g.m;
+  info->part_rank = g.part_rank;
+  info->part_world = g.part_world;
+  info->local_rows = g.local_rows;
+  info->local_edges = g.local_edges;
+  info->heavy_rows = g.n_heavy;
+  info->heavy_edges = g.heavy_edges;
+  info->heavy_segments = g.n_seg;
+  info->sell_rows = g.n_sell;
+  info->sell_slices = g.n_slices;
+  info->sell_entries = g.sell_entries;
+  info->zero_rows = g.n_zero;
+  info->resident_bytes = g.resident_bytes;
+  info->build_ms = g.build_ms;
+  return MGB200_OK;
+}
+
+int mgb200_pagerank_run(mgb200_graph *h, const mgb200_run_params *params, double *rank_out,
+                        mgb200_run_stats *stats_out) {
+  if (!h || !params) return MGB200_ERR_INVALID_ARGUMENT;
+  Graph &g = h->g;
+  if (g.part_world != 1) {
+    set_error("mgb200_pagerank_run needs a single-partition graph; use mgb200_pagerank_run_partition");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  if (g.n > 0 && !rank_out) {
+    set_error("rank_out is null");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  mgb200_run_stats stats{};
+  int rc = iterate(g, *params, stats);
+  if (rc) return rc;
+  if (g.n > 0) {
+    double *d_out = rank_out;
+    if (!params->rank_out_on_device) MGB_CUDA(cudaMalloc(&d_out, g.n * sizeof(double)));
+    rc = launch_write_ranks_original_order(g, d_out);
+    if (!rc && !params->rank_out_on_device) {
+      cudaError_t e = cudaMemcpyAsync(rank_out, d_out, g.n * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+      if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(ranks D2H)", __FILE__, __LINE__);
+    }
+    cudaError_t e = cudaStreamSynchronize(g.stream);
+    if (!rc && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    if (!params->rank_out_on_device) cudaFree(d_out);
+    if (rc) return rc;
+  }
+  if (stats_out) *stats_out = stats;
+  return MGB200_OK;
+}
+
+int mgb200_pagerank_run_partition(mgb200_graph *h, const mgb200_run_params *params, double *rank_out,
+                                  uint32_t *vertex_out, mgb200_run_stats *stats_out) {
+  if (!h || !params) return MGB200_ERR_INVALID_ARGUMENT;
+  Graph &g = h->g;
+  if (g.part_world > 1 && !g.peers_connected) {
+    set_error("partition is not connected to its peers (mgb200_graph_connect_peers)");
+    return MGB200_ERR_COMM;
+  }
+  mgb200_run_stats stats{};
+  int rc = iterate(g, *params, stats);
+  if (rc) return rc;
+  if (g.local_rows > 0 && rank_out) {
+    double *d_out = rank_out;
+    uint32_t *d_vtx = vertex_out;
+    if (!params->rank_out_on_device) {
+      MGB_CUDA(cudaMalloc(&d_out, g.local_rows * sizeof(double)));
+      d_vtx = nullptr;
+    }
+    rc = launch_write_ranks_local(g, d_out, d_vtx);
+    cudaError_t e = cudaSuccess;
+    if (!rc && !params->rank_out_on_device) {
+      e = cudaMemcpyAsync(rank_out, d_out, g.local_rows * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+      if (e == cudaSuccess && vertex_out)
+        e = cudaMemcpyAsync(vertex_out, g.local_vertex, g.local_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            g.stream);
+      if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(ranks D2H)", __FILE__, __LINE__);
+    }
+    e = cudaStreamSynchronize(g.stream);
+    if (!rc && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    if (!params->rank_out_on_device) cudaFree(d_out);
+    if (rc) return rc;
+  }
+  if (stats_out) *stats_out = stats;
+  return MGB200_OK;
+}
+
+int mgb200_parallel_iterative_pagerank(uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
+                                       uint64_t max_iterations, double damping_factor, double stop_epsilon,
+                                       uint32_t number_of_threads, double *rank_out, uint64_t *iterations_out) {
+  // pagerank.cpp:195-197: the thread count is clamped, then zero is rejected before any work.
+  if (number_of_threads == 0) {
+    set_error(MGB200_MSG_ZERO_THREADS);
+    return MGB200_ERR_ZERO_THREADS;
+  }
+  if (n == 0) {
+    if (iterations_out) *iterations_out = max_iterations != 0 ? 1 : 0;
+    // still require a device: the product has no CPU path, even a trivial one
+    int count = 0;
+    int rc = mgb200_device_count(&count);
+    if (rc) return rc;
+    if (count <= 0) {
+      set_error("CUDA error: no CUDA device available (this library has no CPU fallback)");
+      return MGB200_ERR_CUDA;
+    }
+    return MGB200_OK;
+  }
+  const char *dev_env = getenv("MGB200_DEVICE");
+  const int device = dev_env ? atoi(dev_env) : 0;
+  mgb200_graph *g = nullptr;
+  int rc = mgb200_graph_create_host(device, n, m, from, to, 0, 1, &g);
+  if (rc) return rc;
+  mgb200_run_params p{};
+  p.max_iterations = max_iterations;
+  p.damping_factor = damping_factor;
+  p.stop_epsilon = stop_epsilon;
+  mgb200_run_stats stats{};
+  rc = mgb200_pagerank_run(g, &p, rank_out, &stats);
+  mgb200_graph_destroy(g);
+  if (rc) return rc;
+  if (iterations_out) *iterations_out = stats.iterations;
+  return MGB200_OK;
+}
+
+// ---- multi-GPU wiring ---------------------------------------------------------------------------------
+
+int mgb200_graph_export_window(mgb200_graph *h, void *ipc_handle_out) {
+  if (!h || !ipc_handle_out) return MGB200_ERR_INVALID_ARGUMENT;
+  static_assert(sizeof(cudaIpcMemHandle_t) == MGB200_IPC_HANDLE_BYTES, "IPC handle size");
+  MGB_CUDA(cudaSetDevice(h->g.device));
+  cudaIpcMemHandle_t handle;
+  MGB_CUDA(cudaIpcGetMemHandle(&handle, h->g.window));
+  memcpy(ipc_handle_out, &handle, sizeof(handle));
+  return MGB200_OK;
+}
+
+int mgb200_graph_connect_peers(mgb200_graph *h, const void *const *ipc_handles, mgb200_graph *const *peer_graphs) {
+  if (!h) return MGB200_ERR_INVALID_ARGUMENT;
+  Graph &g = h->g;
+  MGB_CUDA(cudaSetDevice(g.device));
+  for (uint32_t q = 0; q < g.part_world; ++q) {
+    if (q == g.part_rank) continue;
+    void *base = nullptr;
+    if (peer_graphs && peer_graphs[q]) {
+      const Graph &pg = peer_graphs[q]->g;
+      if (pg.n != g.n || pg.part_world != g.part_world || pg.part_rank != q) {
+        set_error("peer graph does not belong to the same partitioned graph");
+        return MGB200_ERR_COMM;
+      }
+      if (pg.device != g.device) {
+        int can = 0;
+        MGB_CUDA(cudaDeviceCanAccessPeer(&can, g.device, pg.device));
+        if (!can) {
+          set_error("devices " + std::to_string(g.device) + " and " + std::to_string(pg.device) +
+                    " are not NVLink/P2P peers");
+          return MGB200_ERR_COMM;
+        }
+        cudaError_t e = cudaDeviceEnablePeerAccess(pg.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+        cudaGetLastError();
+      }
+      base = pg.window;
+    } else if (ipc_handles && ipc_handles[q]) {
+      cudaIpcMemHandle_t handle;
+      memcpy(&handle, ipc_handles[q], sizeof(handle));
+      MGB_CUDA(cudaIpcOpenMemHandle(&base, handle, cudaIpcMemLazyEnablePeerAccess));
+      g.peer_mapped[q] = base;
+    } else {
+      set_error("no handle for peer partition " + std::to_string(q));
+      return MGB200_ERR_COMM;
+    }
+    char *bytes = static_cast<char *>(base);
+    g.peers.flags[q] = reinterpret_cast<FlagPage *>(bytes);
+    g.peers.contrib[0][q] = reinterpret_cast<double *>(bytes + kFlagPageBytes);
+    g.peers.contrib[1][q] = reinterpret_cast<double *>(bytes + kFlagPageBytes + g.contrib_stride);
+  }
+  g.peers_connected = true;
+  return MGB200_OK;
+}
+
+// ---- synthetic workload ------------------------------------------------------------------------------
+
+int mgb200_rmat_generate_device(int device, uint32_t scale, uint64_t first_edge, uint64_t count, uint64_t seed,
+                                double a, double b, double c, uint32_t *d_from, uint32_t *d_to) {
+  if (scale == 0 || scale > 31 || (count > 0 && (!d_from || !d_to))) {
+    set_error("rmat: scale must be in [1, 31] and outputs non-null");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  int rc = check_device(device);
+  if (rc) return rc;
+  MGB_CUDA(cudaSetDevice(device));
+  if (count == 0) return MGB200_OK;
+  const RmatThresholds t = rmat_thresholds(a, b, c);
+  const int blocks = static_cast<int>(std::min<uint64_t>((count + 255) / 256, 148ull * 32));
+  rmat_kernel<<<blocks, 256>>>(scale, first_edge, count, seed, t, d_from, d_to);
+  MGB_CUDA(cudaGetLastError());
+  MGB_CUDA(cudaDeviceSynchronize());
+  return MGB200_OK;
+}
+
+int mgb200_rmat_generate_host(uint32_t scale, uint64_t first_edge, uint64_t count, uint64_t seed, double a, double b,
+                              double c, uint64_t *from, uint64_t *to) {
+  if (scale == 0 || scale > 31 || (count > 0 && (!from || !to))) {
+    set_error("rmat: scale must be in [1, 31] and outputs non-null");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  const RmatThresholds t = rmat_thresholds(a, b, c);
+  for (uint64_t i = 0; i < count; ++i) {
+    uint32_t s, d;
+    rmat_edge(scale, first_edge + i, seed, t, s, d);
+    from[i] = s;
+    to[i] = d;
+  }
+  return MGB200_OK;
+}
+
+// ---- device-memory helpers -----------------------------------------------------------------------------
+
+int mgb200_device_malloc(int device, size_t bytes, void **ptr_out) {
+  if (!ptr_out) return MGB200_ERR_INVALID_ARGUMENT;
+  *ptr_out = nullptr;
+  int rc = check_device(device);
+  if (rc) return rc;
+  MGB_CUDA(cudaSetDevice(device));
+  MGB_CUDA(cudaMalloc(ptr_out, bytes ? bytes : 1));
+  return MGB200_OK;
+}
+
+int mgb200_device_free(int device, void *ptr) {
+  int rc = check_device(device);
+  if (rc) return rc;
+  MGB_CUDA(cudaSetDevice(device));
+  MGB_CUDA(cudaFree(ptr));
+  return MGB200_OK;
+}
+
+int mgb200_copy_to_device(int device, void *dst_device, const void *src_host, size_t bytes) {
+  int rc = check_device(device);
+  if (rc) return rc;
+  MGB_CUDA(cudaSetDevice(device));
+  MGB_CUDA(cudaMemcpy(dst_device, src_host, bytes, cudaMemcpyHostToDevice));
+  return MGB200_OK;
+}
+
+int mgb200_copy_to_host(int device, void *dst_host, const void *src_device, size_t bytes) {
+  int rc = check_device(device);
+  if (rc) return rc;
+  MGB_CUDA(cudaSetDevice(device));
+  MGB_CUDA(cudaMemcpy(dst_host, src_device, bytes, cudaMemcpyDeviceToHost));
+  return MGB200_OK;
+}
+
+int mgb200_device_info(int device, char *name_out, size_t name_cap, int *sm_count, size_t *total_bytes) {
+  int rc = check_device(device);
+  if (rc) return rc;
+  cudaDeviceProp prop{};
+  MGB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (name_out && name_cap) {
+    strncpy(name_out, prop.name, name_cap - 1);
+    name_out[name_cap - 1] = '\0';
+  }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (total_bytes) *total_bytes = prop.totalGlobalMem;
+  return MGB200_OK;
+}
+
+}  // extern "C"

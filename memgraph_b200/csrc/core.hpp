@@ -1,0 +1,148 @@
+// memgraph_b200/csrc/core.hpp -- internal types shared by the build, the kernels and the C ABI.
+//
+// HBM layout of one partition (see DESIGN.md "Data layout"):
+//   vertices are relabelled once at ingest: global order = in-degree descending, ties by
+//   out-degree descending, then original id; with P partitions the sorted positions are dealt
+//   round-robin to the P owners and each owner's vertices become one contiguous label range, so
+//   every owner holds an in-degree-sorted slice with ~E/P in-edges and ~N/P rows.
+//   Local rows fall into three classes by in-degree:
+//     heavy  [0, n_heavy)                 deg >= heavy_min_degree : CSC + fixed-size edge segments
+//     sell   [n_heavy, n_heavy + n_sell)  0 < deg < heavy_min    : SELL-32 slices (column-major per 32 rows)
+//     zero   the rest                     deg == 0                : rank is the constant (1-d)/N
+//   contrib[b][label] = rank/out_degree of the vertex with that label for iteration parity b
+//   (full length N + 1, slot N is the zero read by SELL padding entries).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "mgb200_pagerank.h"
+
+namespace mgb200 {
+
+constexpr int kMaxPeers = 8;
+constexpr int kSliceRows = 32;
+
+// Written by iteration kernels, read by the host between batches (plain device memory).
+struct IterState {
+  unsigned long long diff_bits;   // running max |delta| of the current iteration (bits of a double >= 0)
+  unsigned long long iterations;  // completed iterations (the reference's number_of_iterations)
+  unsigned long long barrier_seq; // cross-GPU barrier sequence number (monotonic over the handle's life)
+  double last_diff;
+  double local_sum;               // sum of this partition's un-normalised ranks
+  double rank_sum;                // global sum (NormalizeRank divisor)
+  int done;                       // set when CheckContinueIterate would return false
+  int error;                      // 1: peer barrier timed out
+};
+
+// First page of the exchange window; every slot [q] is written by peer q (remote store over NVLink).
+struct FlagPage {
+  unsigned long long arrive[kMaxPeers];
+  unsigned long long diff_bits[2][kMaxPeers];
+  double rank_sum[2][kMaxPeers];
+};
+constexpr size_t kFlagPageBytes = 4096;
+static_assert(sizeof(FlagPage) <= kFlagPageBytes, "flag page overflow");
+
+struct PeerTable {
+  double *contrib[2][kMaxPeers];  // [parity][peer] -> that peer's contrib buffer (index = global label)
+  FlagPage *flags[kMaxPeers];
+};
+
+struct Graph {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  uint64_t n = 0, m = 0;
+  uint32_t part_rank = 0, part_world = 1;
+  uint64_t row_lo = 0;       // first global label owned
+  uint64_t local_rows = 0;
+  uint64_t local_edges = 0;
+  uint64_t n_heavy = 0, n_sell = 0, n_zero = 0;
+  uint32_t heavy_min_degree = 0, segment_edges = 0;
+
+  // label-space metadata
+  uint32_t *label_of = nullptr;     // [n]  original id -> global label
+  uint32_t *outdeg_l = nullptr;     // [n]  out-degree by global label
+  uint32_t *local_vertex = nullptr; // [local_rows] original id of each owned row
+
+  // heavy class
+  uint64_t heavy_edges = 0;
+  uint64_t *heavy_ptr = nullptr;  // [n_heavy + 1]
+  uint32_t *heavy_idx = nullptr;  // [heavy_edges] source labels, ascending inside a row
+  uint64_t n_seg = 0;
+  uint32_t *seg_row = nullptr;    // [n_seg] local heavy row
+  uint64_t *seg_begin = nullptr;  // [n_seg] first edge
+  uint64_t *seg_first = nullptr;  // [n_heavy + 1] first segment of each heavy row
+  double *seg_partial = nullptr;  // [n_seg]
+
+  // SELL class
+  uint64_t n_slices = 0;
+  uint64_t sell_entries = 0;
+  uint64_t *sell_colbase = nullptr;  // [n_slices + 1] in units of 32-entry columns
+  uint32_t *sell_idx = nullptr;      // [sell_entries] source labels, pad = n
+
+  // iteration state
+  double *rank = nullptr;      // [local_rows] un-normalised ranks, updated in place
+  void *window = nullptr;      // exchange window: FlagPage | contrib[0] | contrib[1]
+  size_t window_bytes = 0;
+  size_t contrib_stride = 0;   // bytes between contrib[0] and contrib[1]
+  IterState *state = nullptr;
+  IterState *host_state = nullptr;  // pinned
+  double *sum_partials = nullptr;   // [kSumBlocks]
+  PeerTable peers{};                // device pointers valid on THIS device
+  void *peer_mapped[kMaxPeers] = {};  // IPC mappings to close
+  bool peers_connected = false;
+
+  uint64_t resident_bytes = 0;
+  double build_ms = 0.0;
+  cudaEvent_t ev[4] = {};
+  // optional per-launch timing of the dominant (SELL) kernel: event pairs around its first launches
+  static constexpr int kMaxTimedLaunches = 64;
+  bool time_spmv = false;
+  int timed_launches = 0;
+  cudaEvent_t kev[2 * kMaxTimedLaunches] = {};
+
+  double *contrib(int parity) const {
+    return reinterpret_cast<double *>(static_cast<char *>(window) + kFlagPageBytes + parity * contrib_stride);
+  }
+  FlagPage *flags() const { return static_cast<FlagPage *>(window); }
+};
+
+// error plumbing (capi.cu)
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+#define MGB_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) return ::mgb200::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+// graph_build.cu
+int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to);
+void free_graph(Graph &g);
+int narrow_edges_u64_to_u32(int device, cudaStream_t stream, uint64_t n, uint64_t count, const uint64_t *d_in,
+                            uint32_t *d_out, int *d_bad_flag);
+
+// pagerank_kernels.cu
+struct IterateConfig {
+  uint64_t max_iterations;
+  double damping;
+  double eps;
+};
+constexpr int kSumBlocks = 1024;
+int launch_init(Graph &g);
+int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *launch_count, uint64_t *spmv_count);
+int launch_barrier(Graph &g);
+int launch_sum_and_exchange(Graph &g);
+int launch_write_ranks_original_order(Graph &g, double *d_out);                   // single partition
+int launch_write_ranks_local(Graph &g, double *d_rank_out, uint32_t *d_vertex_out);  // partitioned
+int kernel_occupancy_report(Graph &g, char *buf, size_t cap);
+
+// rmat.cu
+int rmat_device(int device, uint32_t scale, uint64_t first_edge, uint64_t count, uint64_t seed, double a, double b,
+                double c, uint32_t *d_from, uint32_t *d_to);
+
+}  // namespace mgb200

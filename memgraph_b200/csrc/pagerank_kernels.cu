@@ -1,0 +1,614 @@
+// memgraph_b200/csrc/pagerank_kernels.cu -- the power iteration as hand-written sm_100a kernels.
+//
+// What is computed (reference: mage/cpp/pagerank_module/algorithm/pagerank.cpp):
+//   r_{k+1}[v] = (1-d)/N + d * sum_{(u->v) in E} r_k[u] / outdeg(u)          :86-96, :104-112, :221-226
+//   continue iff k+1 != max_iterations and max_v |r_{k+1}[v] - r_k[v]| > eps  :138-150
+//   result = r_K / sum(r_K)                                                   :156-161
+// The reference pushes along source-ordered edges into per-thread N-vectors; here the same sum is
+// PULLED per destination row from contrib[u] = r_k[u]/outdeg(u), which is computed once per vertex
+// with an IEEE division (bit-identical to the reference's per-edge quotient).  Only the order of
+// the additions inside a row differs from the reference (ascending source label here).
+//
+// Roofline: HBM-bound sparse gather, no tensor cores.  Algorithmic bytes per iteration
+// 12*E + 24*N.  Per edge: one coalesced 4-byte index read (streamed, evict-first) and
+// one 8-byte gather of contrib[]; per row: rank RMW in place, out-degree read, contrib write.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "core.hpp"
+
+namespace mgb200 {
+namespace {
+
+constexpr int kBlockThreads = 256;
+constexpr int kWarpsPerBlock = kBlockThreads / 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kUnroll = 8;
+
+// ---- small PTX helpers ---------------------------------------------------------------------------
+
+// Streaming read of an index word: read once per iteration, keep it out of the way of the
+// gathered vector in L1/L2 (ld.global.nc, no L1 allocation, L2 evict-first policy).
+__device__ __forceinline__ uint64_t make_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint32_t ld_index(const uint32_t *p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+// Gather of one contribution: read-only path; reuse across CTAs lives in L2.
+__device__ __forceinline__ double ld_contrib(const double *p) { return __ldg(p); }
+
+__device__ __forceinline__ int ld_volatile_int(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ---- per-row epilogue ------------------------------------------------------------------------------
+
+struct RowEpilogue {
+  double base;     // (1 - d) / N
+  double damping;  // d
+  double *rank;            // [local_rows]
+  const uint32_t *outdeg;  // [n] by global label
+  uint64_t row_lo;
+  double *contrib_out[kMaxPeers];  // this iteration's output buffer on every partition (self included)
+  int world;
+};
+
+// rank_next = base + d * acc as two separately rounded operations, like the reference's
+// `rank_next[i] += damping_factor * block[i]` compiled without FMA contraction (:109-111).
+__device__ __forceinline__ double finish_row(const RowEpilogue &ep, uint64_t local_row, double acc) {
+  const double next = __dadd_rn(ep.base, __dmul_rn(ep.damping, acc));
+  const double prev = ep.rank[local_row];
+  ep.rank[local_row] = next;
+  const uint64_t label = ep.row_lo + local_row;
+  const uint32_t od = ep.outdeg[label];
+  const double c = od ? __ddiv_rn(next, static_cast<double>(od)) : 0.0;  // :93 quotient, once per vertex
+#pragma unroll
+  for (int q = 0; q < kMaxPeers; ++q) {
+    if (q < ep.world) ep.contrib_out[q][label] = c;  // q != self: remote store over NVLink
+  }
+  return fabs(next - prev);
+}
+
+// max over the block of non-negative, non-NaN doubles -> one atomicMax on the bit pattern.
+__device__ __forceinline__ void block_max_to_state(double local_max, IterState *state) {
+  __shared__ double warp_max[kWarpsPerBlock];
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(kFull, local_max, o);
+    if (other > local_max) local_max = other;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_max[warp] = local_max;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = warp_max[0];
+    for (int w = 1; w < kWarpsPerBlock; ++w)
+      if (warp_max[w] > m) m = warp_max[w];
+    if (m > 0.0) atomicMax(&state->diff_bits, static_cast<unsigned long long>(__double_as_longlong(m)));
+  }
+}
+
+// ---- init -------------------------------------------------------------------------------------------
+
+// rank = 1/N (:199); contrib[0] = (1/N)/outdeg for EVERY label (each partition fills its own full
+// copy, so iteration 0 needs no exchange); pad slots = 0.
+__global__ void __launch_bounds__(kBlockThreads) init_kernel(uint64_t n, uint64_t local_rows, double *rank,
+                                                             const uint32_t *outdeg, double *contrib0,
+                                                             double *contrib1, IterState *state) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const double r0 = 1.0 / static_cast<double>(n);
+  for (uint64_t i = tid; i < n; i += stride) {
+    const uint32_t od = outdeg[i];
+    contrib0[i] = od ? __ddiv_rn(r0, static_cast<double>(od)) : 0.0;
+  }
+  for (uint64_t i = tid; i < local_rows; i += stride) rank[i] = r0;
+  if (tid == 0) {
+    contrib0[n] = 0.0;
+    contrib1[n] = 0.0;
+    state->diff_bits = 0ull;
+    state->iterations = 0ull;
+    state->last_diff = 0.0;
+    state->local_sum = 0.0;
+    state->rank_sum = 0.0;
+    state->done = 0;
+    state->error = 0;
+  }
+}
+
+// ---- SELL-32 rows: one lane per row, coalesced column-major index reads -----------------------------
+
+struct SellArgs {
+  const uint64_t *colbase;
+  const uint32_t *idx;
+  uint64_t n_slices;
+  uint64_t first_row;  // local row of slice 0, lane 0
+  uint64_t end_row;    // first local row past the SELL class
+  const double *contrib_in;
+  IterState *state;
+  RowEpilogue ep;
+};
+
+__global__ void __launch_bounds__(kBlockThreads) sell_rows_kernel(const SellArgs a) {
+  if (ld_volatile_int(&a.state->done)) return;
+  const int lane = threadIdx.x & 31;
+  const uint64_t pol = make_evict_first_policy();
+  const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * kWarpsPerBlock;
+  const uint64_t warp0 = static_cast<uint64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  double local_max = 0.0;
+  for (uint64_t s = warp0; s < a.n_slices; s += warps_total) {
+    const uint64_t c0 = a.colbase[s];
+    const uint32_t width = static_cast<uint32_t>(a.colbase[s + 1] - c0);
+    const uint32_t *p = a.idx + c0 * kSliceRows + lane;
+    double acc = 0.0;
+    uint32_t k = 0;
+    for (; k + kUnroll <= width; k += kUnroll) {
+      uint32_t src[kUnroll];
+      double v[kUnroll];
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) src[j] = ld_index(p + static_cast<size_t>(k + j) * kSliceRows, pol);
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib(a.contrib_in + src[j]);
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) acc += v[j];  // fixed order: ascending source label
+    }
+    if (k < width) {
+      uint32_t src[kUnroll];
+      double v[kUnroll];
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j)
+        if (k + j < width) src[j] = ld_index(p + static_cast<size_t>(k + j) * kSliceRows, pol);
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j)
+        if (k + j < width) v[j] = ld_contrib(a.contrib_in + src[j]);
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j)
+        if (k + j < width) acc += v[j];
+    }
+    const uint64_t row = a.first_row + s * kSliceRows + lane;
+    if (row < a.end_row) {
+      const double d = finish_row(a.ep, row, acc);
+      if (d > local_max) local_max = d;
+    }
+  }
+  block_max_to_state(local_max, a.state);
+}
+
+// ---- heavy rows: one warp per fixed-size edge segment, then one warp per row ------------------------
+
+struct HeavyArgs {
+  const uint64_t *heavy_ptr;
+  const uint32_t *heavy_idx;
+  const uint32_t *seg_row;
+  const uint64_t *seg_begin;
+  const uint64_t *seg_first;
+  double *seg_partial;
+  uint64_t n_seg;
+  uint64_t n_heavy;
+  uint32_t segment_edges;
+  const double *contrib_in;
+  IterState *state;
+  RowEpilogue ep;
+};
+
+__global__ void __launch_bounds__(kBlockThreads) heavy_segments_kernel(const HeavyArgs a) {
+  if (ld_volatile_int(&a.state->done)) return;
+  const int lane = threadIdx.x & 31;
+  const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * kWarpsPerBlock;
+  const uint64_t warp0 = static_cast<uint64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  const uint64_t pol = make_evict_first_policy();
+  for (uint64_t g = warp0; g < a.n_seg; g += warps_total) {
+    const uint32_t r = a.seg_row[g];
+    const uint64_t e0 = a.seg_begin[g];
+    const uint64_t row_end = a.heavy_ptr[r + 1];
+    const uint64_t e1 = (e0 + a.segment_edges < row_end) ? e0 + a.segment_edges : row_end;
+    double acc = 0.0;
+    uint64_t e = e0 + lane;
+    for (; e + 32ull * (kUnroll - 1) < e1; e += 32ull * kUnroll) {
+      uint32_t src[kUnroll];
+      double v[kUnroll];
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) src[j] = ld_index(a.heavy_idx + e + 32ull * j, pol);
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib(a.contrib_in + src[j]);
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) acc += v[j];
+    }
+    for (; e < e1; e += 32) acc += ld_contrib(a.contrib_in + ld_index(a.heavy_idx + e, pol));
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(kFull, acc, o);  // fixed tree
+    if (lane == 0) a.seg_partial[g] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kBlockThreads) heavy_finish_kernel(const HeavyArgs a) {
+  if (ld_volatile_int(&a.state->done)) return;
+  const int lane = threadIdx.x & 31;
+  const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * kWarpsPerBlock;
+  const uint64_t warp0 = static_cast<uint64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  double local_max = 0.0;
+  for (uint64_t r = warp0; r < a.n_heavy; r += warps_total) {
+    const uint64_t s0 = a.seg_first[r], s1 = a.seg_first[r + 1];
+    double acc = 0.0;
+    for (uint64_t s = s0 + lane; s < s1; s += 32) acc += a.seg_partial[s];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(kFull, acc, o);
+    if (lane == 0) {
+      const double d = finish_row(a.ep, r, acc);
+      if (d > local_max) local_max = d;
+    }
+  }
+  block_max_to_state(local_max, a.state);
+}
+
+// ---- zero in-degree rows: rank = (1-d)/N, constant from iteration 1 on -------------------------------
+// Launched for iterations 0 and 1 only, so that BOTH contribution buffers hold base/outdeg.
+__global__ void __launch_bounds__(kBlockThreads) zero_rows_kernel(uint64_t first_row, uint64_t end_row,
+                                                                  IterState *state, const RowEpilogue ep) {
+  if (ld_volatile_int(&state->done)) return;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  double local_max = 0.0;
+  for (uint64_t r = first_row + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < end_row;
+       r += stride) {
+    const double d = finish_row(ep, r, 0.0);
+    if (d > local_max) local_max = d;
+  }
+  block_max_to_state(local_max, state);
+}
+
+// ---- cross-partition barrier over the flag pages (P == 1: degenerates to nothing) ---------------------
+
+struct BarrierArgs {
+  IterState *state;
+  FlagPage *mine;
+  FlagPage *peer[kMaxPeers];  // peer[q] = partition q's flag page as mapped on THIS device (self included)
+  int rank, world;
+  unsigned long long timeout_ns;
+};
+
+// One warp.  Publishes `payload_bits`/`payload_sum` into slot [rank] of every partition's flag page,
+// then waits until every partition has arrived at the same sequence number.  All stores issued by
+// earlier kernels of this stream (including remote contribution stores) are ordered before the
+// release store by the kernel boundary plus the system-scope fence.
+__device__ __forceinline__ bool warp_barrier_exchange(const BarrierArgs &b, unsigned long long seq,
+                                                      unsigned long long payload_bits, double payload_sum) {
+  const int lane = threadIdx.x & 31;
+  const int par = static_cast<int>(seq & 1ull);
+  bool ok = true;
+  if (lane < b.world) {
+    FlagPage *dst = b.peer[lane];
+    st_relaxed_sys_u64(&dst->diff_bits[par][b.rank], payload_bits);
+    st_relaxed_sys_u64(reinterpret_cast<unsigned long long *>(&dst->rank_sum[par][b.rank]),
+                       static_cast<unsigned long long>(__double_as_longlong(payload_sum)));
+    __threadfence_system();
+    st_release_sys_u64(&dst->arrive[b.rank], seq);
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys_u64(&b.mine->arrive[lane]) < seq) {
+      if (global_timer_ns() - t0 > b.timeout_ns) {
+        ok = false;
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  return __all_sync(kFull, ok);
+}
+
+struct IterEndArgs {
+  BarrierArgs bar;
+  unsigned long long max_iterations;
+  double eps;
+};
+
+// End of one iteration: all-reduce(max) of the L-infinity delta across partitions, then the
+// reference's CheckContinueIterate (:138-150) evaluated identically on every partition.
+__global__ void iter_end_kernel(const IterEndArgs a) {
+  IterState *st = a.bar.state;
+  if (ld_volatile_int(&st->done)) return;
+  const int lane = threadIdx.x & 31;
+  unsigned long long bits = st->diff_bits;
+  bool ok = true;
+  unsigned long long seq = st->barrier_seq;
+  if (a.bar.world > 1) {
+    seq += 1;
+    ok = warp_barrier_exchange(a.bar, seq, bits, 0.0);
+    unsigned long long other = 0ull;
+    if (lane < a.bar.world) other = a.bar.mine->diff_bits[seq & 1ull][lane];
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long t = __shfl_xor_sync(kFull, other, o);
+      if (t > other) other = t;
+    }
+    bits = other;
+  }
+  if (lane == 0) {
+    st->barrier_seq = seq;
+    const double diff = __longlong_as_double(static_cast<long long>(bits));
+    st->iterations += 1ull;
+    st->last_diff = diff;
+    const bool cont = (st->iterations != a.max_iterations) && (diff > a.eps);
+    st->diff_bits = 0ull;
+    if (!ok) st->error = 1;
+    if (!cont || !ok) st->done = 1;
+  }
+}
+
+__global__ void barrier_kernel(const BarrierArgs b) {
+  if (b.world <= 1) return;
+  IterState *st = b.state;
+  const unsigned long long seq = st->barrier_seq + 1;
+  const bool ok = warp_barrier_exchange(b, seq, 0ull, 0.0);
+  if ((threadIdx.x & 31) == 0) {
+    st->barrier_seq = seq;
+    if (!ok) {
+      st->error = 1;
+      st->done = 1;
+    }
+  }
+}
+
+// ---- normalise (:156-161): deterministic two-stage sum, then divide ----------------------------------
+
+__global__ void __launch_bounds__(kBlockThreads) partial_sum_kernel(const double *rank, uint64_t count,
+                                                                    double *partials) {
+  // block b sums the contiguous chunk [b*chunk, (b+1)*chunk): thread-strided partials, fixed tree.
+  const uint64_t chunk = (count + gridDim.x - 1) / gridDim.x;
+  const uint64_t lo = chunk * blockIdx.x;
+  const uint64_t hi = (lo + chunk < count) ? lo + chunk : count;
+  double acc = 0.0;
+  for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += rank[i];
+  __shared__ double sm[kBlockThreads];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = kBlockThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
+}
+
+__global__ void final_sum_kernel(const double *partials, int count, const BarrierArgs b) {
+  __shared__ double sm[kSumBlocks];
+  for (int i = threadIdx.x; i < kSumBlocks; i += blockDim.x) sm[i] = i < count ? partials[i] : 0.0;
+  __syncthreads();
+  for (int o = kSumBlocks / 2; o > 0; o >>= 1) {
+    for (int i = threadIdx.x; i < o; i += blockDim.x) sm[i] += sm[i + o];
+    __syncthreads();
+  }
+  IterState *st = b.state;
+  if (threadIdx.x < 32) {
+    const double local = sm[0];
+    double total = local;
+    bool ok = true;
+    unsigned long long seq = st->barrier_seq;
+    if (b.world > 1) {
+      seq += 1;
+      ok = warp_barrier_exchange(b, seq, 0ull, local);
+      total = 0.0;
+      for (int q = 0; q < b.world; ++q) total += b.mine->rank_sum[seq & 1ull][q];  // same order everywhere
+    }
+    if (threadIdx.x == 0) {
+      st->barrier_seq = seq;
+      st->local_sum = local;
+      st->rank_sum = total;
+      if (!ok) st->error = 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlockThreads) write_original_order_kernel(uint64_t n, const uint32_t *label_of,
+                                                                             const double *rank,
+                                                                             const IterState *state, double *out) {
+  const double sum = state->rank_sum;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t v = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < n; v += stride)
+    out[v] = __ddiv_rn(rank[label_of[v]], sum);  // :158-160
+}
+
+__global__ void __launch_bounds__(kBlockThreads) write_local_kernel(uint64_t local_rows, const double *rank,
+                                                                    const uint32_t *local_vertex,
+                                                                    const IterState *state, double *out,
+                                                                    uint32_t *vertex_out) {
+  const double sum = state->rank_sum;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t r = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < local_rows; r += stride) {
+    out[r] = __ddiv_rn(rank[r], sum);
+    if (vertex_out) vertex_out[r] = local_vertex[r];
+  }
+}
+
+// ---- host-side launch helpers -------------------------------------------------------------------------
+
+int grid_for(const Graph &g, const void *kernel, uint64_t work_items_per_block_hint = 0) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockThreads, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 4;
+  (void)work_items_per_block_hint;
+  return g.sm_count * per_sm;  // a whole number of resident waves on 148 SMs
+}
+
+uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+RowEpilogue make_epilogue(const Graph &g, uint64_t it, const IterateConfig &cfg) {
+  RowEpilogue ep{};
+  ep.base = (1.0 - cfg.damping) / static_cast<double>(g.n);
+  ep.damping = cfg.damping;
+  ep.rank = g.rank;
+  ep.outdeg = g.outdeg_l;
+  ep.row_lo = g.row_lo;
+  ep.world = static_cast<int>(g.part_world);
+  const int out_parity = static_cast<int>((it + 1) & 1ull);
+  for (int q = 0; q < kMaxPeers; ++q) ep.contrib_out[q] = q < ep.world ? g.peers.contrib[out_parity][q] : nullptr;
+  return ep;
+}
+
+unsigned long long barrier_timeout_ns() {
+  static unsigned long long cached = 0;
+  if (!cached) {
+    const char *s = getenv("MGB200_BARRIER_TIMEOUT_MS");
+    unsigned long long ms = s ? strtoull(s, nullptr, 10) : 20000ull;
+    if (ms == 0) ms = 20000ull;
+    cached = ms * 1000000ull;
+  }
+  return cached;
+}
+
+BarrierArgs make_barrier(const Graph &g) {
+  BarrierArgs b{};
+  b.state = g.state;
+  b.mine = g.flags();
+  b.rank = static_cast<int>(g.part_rank);
+  b.world = static_cast<int>(g.part_world);
+  for (int q = 0; q < kMaxPeers; ++q) b.peer[q] = q < b.world ? g.peers.flags[q] : nullptr;
+  b.timeout_ns = barrier_timeout_ns();
+  return b;
+}
+
+}  // namespace
+
+int launch_init(Graph &g) {
+  MGB_CUDA(cudaSetDevice(g.device));
+  const int grid = grid_for(g, reinterpret_cast<const void *>(init_kernel));
+  init_kernel<<<grid, kBlockThreads, 0, g.stream>>>(g.n, g.local_rows, g.rank, g.outdeg_l, g.contrib(0),
+                                                     g.contrib(1), g.state);
+  MGB_CUDA(cudaGetLastError());
+  return MGB200_OK;
+}
+
+int launch_barrier(Graph &g) {
+  if (g.part_world <= 1) return MGB200_OK;
+  barrier_kernel<<<1, 32, 0, g.stream>>>(make_barrier(g));
+  MGB_CUDA(cudaGetLastError());
+  return MGB200_OK;
+}
+
+// One iteration = zero rows (iterations 0 and 1 only) + SELL rows + heavy segments + heavy finish
+// + iteration end.  Every kernel returns immediately once state->done is set, so the host may
+// enqueue iterations ahead of the convergence decision.
+int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *launch_count,
+                     uint64_t *spmv_count) {
+  const RowEpilogue ep = make_epilogue(g, it, cfg);
+  const double *contrib_in = g.contrib(static_cast<int>(it & 1ull));
+  uint64_t launches = 0;
+  if (g.n_zero > 0 && it < 2) {
+    const uint64_t first = g.n_heavy + g.n_sell;
+    const int grid = static_cast<int>(
+        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(zero_rows_kernel))),
+            ceil_div(g.n_zero, kBlockThreads)));
+    zero_rows_kernel<<<grid, kBlockThreads, 0, g.stream>>>(first, first + g.n_zero, g.state, ep);
+    ++launches;
+  }
+  if (g.n_seg > 0) {
+    HeavyArgs h{};
+    h.heavy_ptr = g.heavy_ptr;
+    h.heavy_idx = g.heavy_idx;
+    h.seg_row = g.seg_row;
+    h.seg_begin = g.seg_begin;
+    h.seg_first = g.seg_first;
+    h.seg_partial = g.seg_partial;
+    h.n_seg = g.n_seg;
+    h.n_heavy = g.n_heavy;
+    h.segment_edges = g.segment_edges;
+    h.contrib_in = contrib_in;
+    h.state = g.state;
+    h.ep = ep;
+    int grid = static_cast<int>(
+        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_segments_kernel))),
+            ceil_div(g.n_seg, kWarpsPerBlock)));
+    heavy_segments_kernel<<<grid, kBlockThreads, 0, g.stream>>>(h);
+    grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_finish_kernel))),
+                                ceil_div(g.n_heavy, kWarpsPerBlock)));
+    heavy_finish_kernel<<<grid, kBlockThreads, 0, g.stream>>>(h);
+    launches += 2;
+  }
+  if (g.n_slices > 0) {
+    SellArgs s{};
+    s.colbase = g.sell_colbase;
+    s.idx = g.sell_idx;
+    s.n_slices = g.n_slices;
+    s.first_row = g.n_heavy;
+    s.end_row = g.n_heavy + g.n_sell;
+    s.contrib_in = contrib_in;
+    s.state = g.state;
+    s.ep = ep;
+    const int grid = static_cast<int>(
+        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_rows_kernel))),
+            ceil_div(g.n_slices, kWarpsPerBlock)));
+    const bool timed = g.time_spmv && g.timed_launches < Graph::kMaxTimedLaunches;
+    if (timed) MGB_CUDA(cudaEventRecord(g.kev[2 * g.timed_launches], g.stream));
+    sell_rows_kernel<<<grid, kBlockThreads, 0, g.stream>>>(s);
+    if (timed) {
+      MGB_CUDA(cudaEventRecord(g.kev[2 * g.timed_launches + 1], g.stream));
+      ++g.timed_launches;
+    }
+    ++launches;
+    if (spmv_count) *spmv_count += 1;
+  }
+  IterEndArgs e{};
+  e.bar = make_barrier(g);
+  e.max_iterations = cfg.max_iterations;
+  e.eps = cfg.eps;
+  iter_end_kernel<<<1, 32, 0, g.stream>>>(e);
+  ++launches;
+  MGB_CUDA(cudaGetLastError());
+  if (launch_count) *launch_count += launches;
+  return MGB200_OK;
+}
+
+int launch_sum_and_exchange(Graph &g) {
+  const int blocks = static_cast<int>(std::min<uint64_t>(kSumBlocks, g.local_rows ? ceil_div(g.local_rows, 4096) : 1));
+  partial_sum_kernel<<<blocks, kBlockThreads, 0, g.stream>>>(g.rank, g.local_rows, g.sum_partials);
+  final_sum_kernel<<<1, 256, 0, g.stream>>>(g.sum_partials, blocks, make_barrier(g));
+  MGB_CUDA(cudaGetLastError());
+  return MGB200_OK;
+}
+
+int launch_write_ranks_original_order(Graph &g, double *d_out) {
+  if (g.n == 0) return MGB200_OK;
+  const int grid = static_cast<int>(
+      std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(write_original_order_kernel))),
+          ceil_div(g.n, kBlockThreads)));
+  write_original_order_kernel<<<grid, kBlockThreads, 0, g.stream>>>(g.n, g.label_of, g.rank, g.state, d_out);
+  MGB_CUDA(cudaGetLastError());
+  return MGB200_OK;
+}
+
+int launch_write_ranks_local(Graph &g, double *d_rank_out, uint32_t *d_vertex_out) {
+  if (g.local_rows == 0) return MGB200_OK;
+  const int grid = static_cast<int>(
+      std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(write_local_kernel))),
+          ceil_div(g.local_rows, kBlockThreads)));
+  write_local_kernel<<<grid, kBlockThreads, 0, g.stream>>>(g.local_rows, g.rank, g.local_vertex, g.state,
+                                                           d_rank_out, d_vertex_out);
+  MGB_CUDA(cudaGetLastError());
+  return MGB200_OK;
+}
+
+int kernel_occupancy_report(Graph &g, char *buf, size_t cap) {
+  int a = 0, b = 0, c = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sell_rows_kernel, kBlockThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, heavy_segments_kernel, kBlockThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, heavy_finish_kernel, kBlockThreads, 0);
+  snprintf(buf, cap, "sm=%d blocks/SM: sell=%d heavy_seg=%d heavy_fin=%d (block=%d threads)", g.sm_count, a, b, c,
+           kBlockThreads);
+  return MGB200_OK;
+}
+
+}  // namespace mgb200
