@@ -1,0 +1,132 @@
+"""ctypes front-end of memgraph_b200/_build/libmgp_fake_host.so (the in-memory mgp host, test
+infrastructure).  Loaded RTLD_GLOBAL so that query modules dlopen'ed through it bind their
+undefined mgp_* symbols to it, like they bind to the memgraph executable."""
+import ctypes
+import os
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_SO = os.path.join(REPO, "memgraph_b200", "_build", "libmgp_fake_host.so")
+MODULE_SO = os.path.join(REPO, "memgraph_b200", "_build", "pagerank.so")
+REF_MODULE_SO = os.path.join(REPO, "oracle", "_ref", "pagerank_reference.so")
+
+_host = None
+
+
+def host():
+    global _host
+    if _host is None:
+        if not os.path.exists(HOST_SO):
+            from memgraph_b200 import build
+            build.build_all()
+        H = ctypes.CDLL(HOST_SO, mode=ctypes.RTLD_GLOBAL)
+        vp, i64p, f64p = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p
+        H.fh_graph_create.restype = vp
+        H.fh_graph_create.argtypes = [ctypes.c_uint64, i64p, ctypes.c_uint64, i64p, i64p, ctypes.c_int]
+        H.fh_graph_destroy.argtypes = [vp]
+        H.fh_graph_set_abort.argtypes = [vp, ctypes.c_int]
+        H.fh_graph_abort_polls.restype = ctypes.c_long
+        H.fh_graph_abort_polls.argtypes = [vp]
+        H.fh_graph_hide_vertex.argtypes = [vp, ctypes.c_int64]
+        H.fh_live_objects.restype = ctypes.c_long
+        H.fh_module_load.restype = vp
+        H.fh_module_load.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+        H.fh_module_close.argtypes = [vp]
+        H.fh_module_signature.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+        H.fh_call.restype = vp
+        H.fh_call.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p]
+        H.fh_result_error.restype = ctypes.c_char_p
+        H.fh_result_error.argtypes = [vp]
+        H.fh_result_rows.restype = ctypes.c_uint64
+        H.fh_result_rows.argtypes = [vp]
+        H.fh_result_copy.argtypes = [vp, ctypes.c_void_p, ctypes.c_void_p]
+        H.fh_result_destroy.argtypes = [vp]
+        _host = H
+    return _host
+
+
+class ProcedureError(RuntimeError):
+    """What the engine raises as QueryRuntimeException("<module>.<proc>: <msg>")."""
+
+
+class Graph:
+    def __init__(self, gids, src_gid, dst_gid, transactional=True):
+        g = np.ascontiguousarray(gids, dtype=np.int64)
+        s = np.ascontiguousarray(src_gid, dtype=np.int64)
+        d = np.ascontiguousarray(dst_gid, dtype=np.int64)
+        self.h = host().fh_graph_create(len(g), g.ctypes.data, len(s), s.ctypes.data, d.ctypes.data,
+                                        1 if transactional else 0)
+        if not self.h:
+            raise ValueError("edge endpoint is not a vertex of the graph")
+
+    def set_abort(self, flag=True):
+        host().fh_graph_set_abort(self.h, 1 if flag else 0)
+
+    def abort_polls(self):
+        return host().fh_graph_abort_polls(self.h)
+
+    def hide_vertex(self, gid):
+        assert host().fh_graph_hide_vertex(self.h, gid) == 0
+
+    def close(self):
+        if self.h:
+            host().fh_graph_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class Module:
+    """A loaded query module (SharedLibraryModule)."""
+
+    def __init__(self, path):
+        err = ctypes.create_string_buffer(1024)
+        self.h = host().fh_module_load(path.encode(), err, 1024)
+        if not self.h:
+            raise OSError(err.value.decode())
+
+    def signature(self, proc="get"):
+        buf = ctypes.create_string_buffer(1024)
+        if host().fh_module_signature(self.h, proc.encode(), buf, 1024):
+            raise KeyError(proc)
+        return buf.value.decode()
+
+    def call(self, graph, *args, proc="get"):
+        """args: Python ints are INTEGER literals, floats are FLOAT literals (strictly typed).
+        Returns (node_gids, ranks) in emission order."""
+        kinds = "".join("i" if isinstance(a, (int, np.integer)) and not isinstance(a, bool) else "d" for a in args)
+        iv = np.array([int(a) if k == "i" else 0 for a, k in zip(args, kinds)] + [0], dtype=np.int64)
+        dv = np.array([float(a) if k == "d" else 0.0 for a, k in zip(args, kinds)] + [0.0], dtype=np.float64)
+        r = host().fh_call(self.h, proc.encode(), graph.h, len(args), kinds.encode(), iv.ctypes.data, dv.ctypes.data)
+        try:
+            err = host().fh_result_error(r)
+            if err is not None:
+                raise ProcedureError(err.decode())
+            n = host().fh_result_rows(r)
+            nodes = np.zeros(n, dtype=np.int64)
+            ranks = np.zeros(n, dtype=np.float64)
+            host().fh_result_copy(r, nodes.ctypes.data, ranks.ctypes.data)
+            return nodes, ranks
+        finally:
+            host().fh_result_destroy(r)
+
+    def close(self):
+        if self.h:
+            rc = host().fh_module_close(self.h)
+            self.h = None
+            return rc
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def live_objects():
+    return host().fh_live_objects()
