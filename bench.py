@@ -279,6 +279,12 @@ def run_b200_arm(args):
     assert iters == ITERATIONS, f"executed {iters} iterations, expected {ITERATIONS}"
     value = m * ITERATIONS * args.steps / (total_ms * 1e-3)
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "scale": scale, "ms_per_iteration": total_ms / args.steps / ITERATIONS,
+                              "edges_per_s": value, "sell_kernel_ms": kernel_ms / max(kernel_launches, 1),
+                              "tag": os.environ.get("MGB200_TAG", "")}), flush=True)
+        return 0
     # e2e: the public call with a HOST output buffer (D2H of the ranks inside the timed region)
     e2e = None
     if world == 1:
@@ -385,6 +391,7 @@ def main():
     ap.add_argument("--cpu-scale", type=int, default=int(os.environ.get("MGB200_CPU_SCALE", "22")),
                     help="RMAT scale of the bounded CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="sweep mode: device-resident timing only, compact JSON")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

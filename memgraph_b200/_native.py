@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libmgb200_pagerank.so")
+LIB_PATH = os.environ.get("MGB200_LIBRARY") or os.path.join(_HERE, "_build", "libmgb200_pagerank.so")
 
 u64, u32, f64, i32 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_double, ctypes.c_int
 vp = ctypes.c_void_p

@@ -83,6 +83,9 @@ struct Graph {
   uint64_t sell_entries = 0;
   uint64_t *sell_colbase = nullptr;  // [n_slices + 1] in units of 32-entry columns
   uint32_t *sell_idx = nullptr;      // [sell_entries] source labels, pad = n
+  double *sell_sums = nullptr;       // [n_sell] per-row gathered sums of the current iteration
+  uint32_t sell_items = 0;           // work items of the streaming kernel: contiguous slice runs, ~equal columns
+  uint64_t *sell_item_begin = nullptr;  // [sell_items + 1] first slice of each item
 
   // iteration state
   double *rank = nullptr;      // [local_rows] un-normalised ranks, updated in place

@@ -199,6 +199,26 @@ __global__ void sell_fill_kernel(uint64_t n_slices, uint64_t first_row, uint64_t
   }
 }
 
+// work items for the streaming SELL kernel: item i starts at the first slice whose column base is
+// >= i * total_cols / n_items (binary search over the slice column bases)
+__global__ void sell_items_kernel(uint32_t n_items, uint64_t n_slices, const uint64_t *colbase, uint64_t total_cols,
+                                  uint64_t *item_begin) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_items) return;
+  if (i == n_items) {
+    item_begin[i] = n_slices;
+    return;
+  }
+  const unsigned __int128 t = static_cast<unsigned __int128>(total_cols) * i;
+  const uint64_t target = static_cast<uint64_t>(t / n_items);
+  uint64_t lo = 0, hi = n_slices;  // first s in [0, n_slices] with colbase[s] >= target
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (colbase[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  item_begin[i] = lo;
+}
+
 __global__ void gather_local_vertex_kernel(uint64_t rows, uint64_t row_lo, const uint32_t *vertex_of_label,
                                            uint32_t *local_vertex) {
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
@@ -277,6 +297,8 @@ void free_graph(Graph &g) {
   cudaSetDevice(g.device);
   for (int q = 0; q < kMaxPeers; ++q)
     if (g.peer_mapped[q]) cudaIpcCloseMemHandle(g.peer_mapped[q]);
+  if (g.sell_item_begin) cudaFree(g.sell_item_begin);
+  if (g.sell_sums) cudaFree(g.sell_sums);
   void *ptrs[] = {g.label_of,  g.outdeg_l,  g.local_vertex, g.heavy_ptr,    g.heavy_idx, g.seg_row,     g.seg_begin,
                   g.seg_first, g.seg_partial, g.sell_colbase, g.sell_idx,     g.rank,      g.window,      g.state,
                   g.sum_partials};
@@ -494,6 +516,11 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     sell_fill_kernel<<<blocks_for(g.n_slices * 32, g.sm_count), kThreads, 0, st>>>(
         g.n_slices, g.n_heavy, g.n_heavy + g.n_sell, row_ptr, ekey, g.sell_colbase, static_cast<uint32_t>(n),
         g.sell_idx);
+    MGB_CUDA(keep_alloc(g, &g.sell_sums, g.n_sell));
+    g.sell_items = env_u32("MGB200_SELL_ITEMS", static_cast<uint32_t>(g.sm_count) * 32u);
+    MGB_CUDA(keep_alloc(g, &g.sell_item_begin, static_cast<uint64_t>(g.sell_items) + 1));
+    sell_items_kernel<<<(g.sell_items + 1 + kThreads - 1) / kThreads, kThreads, 0, st>>>(
+        g.sell_items, g.n_slices, g.sell_colbase, total_cols, g.sell_item_begin);
   }
   MGB_CUDA(cudaGetLastError());
   MGB_CUDA(cudaEventRecord(g.ev[1], st));

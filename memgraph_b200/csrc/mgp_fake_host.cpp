@@ -46,7 +46,7 @@ struct FakeGraphData {
   std::vector<int64_t> gids;                 // ascending, like Vertices(view) over in-memory storage
   std::vector<std::vector<uint32_t>> out;    // out[v] = indices of destination vertices, insertion order
   std::unordered_map<int64_t, uint32_t> index_of;
-  std::vector<char> hidden;                  // hidden[v] != 0: FindVertex fails (vanished in analytical mode)
+  std::vector<char> hidden;                  // hidden[v] != 0: FindVertex fails at emission (vertex vanished mid-call, analytical mode)
   uint64_t edge_count = 0;
   int transactional = 1;
   std::atomic<int> abort_flag{0};
@@ -256,7 +256,6 @@ void mgp_vertex_destroy(mgp_vertex *v) {
 }
 mgp_error mgp_vertex_iter_out_edges(mgp_vertex *v, mgp_memory *memory, mgp_edges_iterator **result) {
   if (memory) memory->allocations++;
-  if (v->graph->data->hidden[v->index]) return mgp_error::MGP_ERROR_DELETED_OBJECT;
   auto *it = new (std::nothrow) mgp_edges_iterator();
   if (!it) return mgp_error::MGP_ERROR_UNABLE_TO_ALLOCATE;
   it->graph = v->graph;

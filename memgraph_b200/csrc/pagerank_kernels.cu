@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "core.hpp"
 
@@ -24,7 +25,10 @@ namespace {
 constexpr int kBlockThreads = 256;
 constexpr int kWarpsPerBlock = kBlockThreads / 32;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kUnroll = 8;
+#ifndef MGB_UNROLL
+#define MGB_UNROLL 8
+#endif
+constexpr int kUnroll = MGB_UNROLL;
 
 // ---- small PTX helpers ---------------------------------------------------------------------------
 
@@ -35,13 +39,76 @@ __device__ __forceinline__ uint64_t make_evict_first_policy() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+#ifndef MGB_IDX_HINT
+#define MGB_IDX_HINT 1     // 1: index stream no L1 allocation + L2 evict_first, 0: plain read-only loads
+#endif
+#ifndef MGB_EPI_HINT
+#define MGB_EPI_HINT 1     // 1: rank / out-degree / contrib_out traffic evict_first, 0: default policy
+#endif
+#ifndef MGB_GATHER_POLICY
+#define MGB_GATHER_POLICY 1  // 0: plain ld.global.nc, 1: range(evict_last hot prefix, evict_first tail), 2: all evict_last
+#endif
 __device__ __forceinline__ uint32_t ld_index(const uint32_t *p, uint64_t pol) {
+#if MGB_IDX_HINT
   uint32_t v;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
   return v;
+#else
+  (void)pol;
+  return __ldg(p);
+#endif
 }
 // Gather of one contribution: read-only path; reuse across CTAs lives in L2.
-__device__ __forceinline__ double ld_contrib(const double *p) { return __ldg(p); }
+#ifndef MGB_EXP
+#define MGB_EXP 0  // timing-attribution experiments (WRONG RESULTS): 1 no epilogue, 2 gathers forced into 8 MiB,
+#endif             // 3 no index stream (computed indices), 4 = 2+3, 5 = 1+2+3
+__device__ __forceinline__ double ld_contrib(const double *p, uint64_t pol) {
+#if MGB_GATHER_POLICY
+  double v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+#else
+  (void)pol;
+  return __ldg(p);
+#endif
+}
+// L2 residency plan (measured, scripts/l2_bench.cu): random gathers run at ~275 G/s while the gathered
+// set fits ~64 MiB of L2 and at ~49 G/s from HBM.  Labels are sorted by degree, so the hot vertices are
+// the PREFIX of contrib[]: that prefix is loaded evict_last, everything else that streams through L2
+// (cold tail of contrib[], index arrays, rank / out-degree / contrib_out traffic) is evict_first.
+struct GatherWindow {
+  uint32_t hot_bytes;    // primary (evict_last) span, from contrib_in
+  uint32_t total_bytes;  // whole vector (secondary span: evict_first)
+};
+__device__ __forceinline__ uint64_t make_gather_policy(const double *contrib_in, GatherWindow w) {
+  uint64_t pol;
+#if MGB_GATHER_POLICY == 2
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#else
+  asm volatile("createpolicy.range.global.L2::evict_last.L2::evict_first.b64 %0, [%1], %2, %3;"
+               : "=l"(pol)
+               : "l"(contrib_in), "r"(w.hot_bytes), "r"(w.total_bytes));
+#endif
+  return pol;
+}
+__device__ __forceinline__ double ld_stream_f64(const double *p, uint64_t pol) {
+#if MGB_EPI_HINT
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+#else
+  (void)pol;
+  return *p;
+#endif
+}
+__device__ __forceinline__ void st_stream_f64(double *p, double v, uint64_t pol) {
+#if MGB_EPI_HINT
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+#else
+  (void)pol;
+  *p = v;
+#endif
+}
 
 __device__ __forceinline__ int ld_volatile_int(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 
@@ -76,16 +143,17 @@ struct RowEpilogue {
 
 // rank_next = base + d * acc as two separately rounded operations, like the reference's
 // `rank_next[i] += damping_factor * block[i]` compiled without FMA contraction (:109-111).
-__device__ __forceinline__ double finish_row(const RowEpilogue &ep, uint64_t local_row, double acc) {
+__device__ __forceinline__ double finish_row(const RowEpilogue &ep, uint64_t local_row, double acc,
+                                             uint64_t stream_pol) {
   const double next = __dadd_rn(ep.base, __dmul_rn(ep.damping, acc));
-  const double prev = ep.rank[local_row];
-  ep.rank[local_row] = next;
+  const double prev = ld_stream_f64(ep.rank + local_row, stream_pol);
+  st_stream_f64(ep.rank + local_row, next, stream_pol);
   const uint64_t label = ep.row_lo + local_row;
-  const uint32_t od = ep.outdeg[label];
+  const uint32_t od = ld_index(ep.outdeg + label, stream_pol);
   const double c = od ? __ddiv_rn(next, static_cast<double>(od)) : 0.0;  // :93 quotient, once per vertex
 #pragma unroll
   for (int q = 0; q < kMaxPeers; ++q) {
-    if (q < ep.world) ep.contrib_out[q][label] = c;  // q != self: remote store over NVLink
+    if (q < ep.world) st_stream_f64(ep.contrib_out[q] + label, c, stream_pol);  // q != self: NVLink store
   }
   return fabs(next - prev);
 }
@@ -145,30 +213,97 @@ struct SellArgs {
   uint64_t first_row;  // local row of slice 0, lane 0
   uint64_t end_row;    // first local row past the SELL class
   const double *contrib_in;
+  GatherWindow window;
   IterState *state;
-  RowEpilogue ep;
+  double *sums;  // [n_sell] per-row sums of gathered contributions (consumed by sell_epilogue_kernel)
 };
 
-__global__ void __launch_bounds__(kBlockThreads) sell_rows_kernel(const SellArgs a) {
+// Row epilogue of the SELL class as a separate, perfectly coalesced elementwise pass.  Fusing it into
+// the gather kernels cost 2.9 ms of 5.2 ms at scale-26 (profiles/r01_attribution.md): the rank and
+// out-degree loads, the FP64 division and the stores sit at the end of every slice's dependency chain and
+// drain the warp's memory pipeline once per ~24 columns.  Split, it is ~0.2 ms of pure streaming.
+__global__ void __launch_bounds__(kBlockThreads) sell_epilogue_kernel(uint64_t first_row, uint64_t end_row,
+                                                                      const double *sums, IterState *state,
+                                                                      const RowEpilogue ep) {
+  if (ld_volatile_int(&state->done)) return;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const uint64_t pol = make_evict_first_policy();
+  double local_max = 0.0;
+  for (uint64_t r = first_row + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < end_row;
+       r += stride) {
+    const double d = finish_row(ep, r, ld_stream_f64(sums + (r - first_row), pol), pol);
+    if (d > local_max) local_max = d;
+  }
+  block_max_to_state(local_max, state);
+}
+
+// Tunables (compile-time, see profiles/ for the sweep that picked the defaults)
+#ifndef MGB_SELL_MIN_BLOCKS
+#define MGB_SELL_MIN_BLOCKS 4  // resident CTAs/SM requested from ptxas (register cap = 65536 / (256 * this))
+#endif
+#ifndef MGB_SELL_PREFETCH
+#define MGB_SELL_PREFETCH 0    // 1: load the next batch of column indices before consuming the current gathers
+#endif
+
+__global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_kernel(const SellArgs a) {
   if (ld_volatile_int(&a.state->done)) return;
   const int lane = threadIdx.x & 31;
   const uint64_t pol = make_evict_first_policy();
+  const uint64_t gpol = make_gather_policy(a.contrib_in, a.window);
   const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * kWarpsPerBlock;
   const uint64_t warp0 = static_cast<uint64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-  double local_max = 0.0;
+  uint64_t c0 = 0, c1 = 0;
+  if (warp0 < a.n_slices) {
+    c0 = a.colbase[warp0];
+    c1 = a.colbase[warp0 + 1];
+  }
   for (uint64_t s = warp0; s < a.n_slices; s += warps_total) {
-    const uint64_t c0 = a.colbase[s];
-    const uint32_t width = static_cast<uint32_t>(a.colbase[s + 1] - c0);
+    const uint32_t width = static_cast<uint32_t>(c1 - c0);
     const uint32_t *p = a.idx + c0 * kSliceRows + lane;
+    const uint64_t cbase = c0;
+    (void)cbase;
+    // slice descriptor of this warp's NEXT slice: issued now, consumed after this slice's gathers
+    const uint64_t s_next = s + warps_total;
+    if (s_next < a.n_slices) {
+      c0 = a.colbase[s_next];
+      c1 = a.colbase[s_next + 1];
+    }
     double acc = 0.0;
     uint32_t k = 0;
+#if MGB_SELL_PREFETCH
+    uint32_t nxt[kUnroll];
+    if (width >= kUnroll) {
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) nxt[j] = ld_index(p + static_cast<size_t>(j) * kSliceRows, pol);
+    }
+#endif
     for (; k + kUnroll <= width; k += kUnroll) {
       uint32_t src[kUnroll];
       double v[kUnroll];
+#if MGB_SELL_PREFETCH
 #pragma unroll
-      for (int j = 0; j < kUnroll; ++j) src[j] = ld_index(p + static_cast<size_t>(k + j) * kSliceRows, pol);
+      for (int j = 0; j < kUnroll; ++j) src[j] = nxt[j];
+      if (k + 2 * kUnroll <= width) {
 #pragma unroll
-      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib(a.contrib_in + src[j]);
+        for (int j = 0; j < kUnroll; ++j)
+          nxt[j] = ld_index(p + static_cast<size_t>(k + kUnroll + j) * kSliceRows, pol);
+      }
+#else
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) {
+#if MGB_EXP == 3 || MGB_EXP == 4 || MGB_EXP == 5
+        src[j] = static_cast<uint32_t>(((cbase + k + j) * 32 + lane) * 2654435761u) % a.window.hot_bytes;
+        src[j] = static_cast<uint32_t>((static_cast<uint64_t>(src[j]) * src[j]) % (a.window.total_bytes / 8));
+#else
+        src[j] = ld_index(p + static_cast<size_t>(k + j) * kSliceRows, pol);
+#endif
+#if MGB_EXP == 2 || MGB_EXP == 4 || MGB_EXP == 5
+        src[j] &= 0xFFFFFu;
+#endif
+      }
+#endif
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib(a.contrib_in + src[j], gpol);
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) acc += v[j];  // fixed order: ascending source label
     }
@@ -180,19 +315,17 @@ __global__ void __launch_bounds__(kBlockThreads) sell_rows_kernel(const SellArgs
         if (k + j < width) src[j] = ld_index(p + static_cast<size_t>(k + j) * kSliceRows, pol);
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j)
-        if (k + j < width) v[j] = ld_contrib(a.contrib_in + src[j]);
+        if (k + j < width) v[j] = ld_contrib(a.contrib_in + src[j], gpol);
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j)
         if (k + j < width) acc += v[j];
     }
     const uint64_t row = a.first_row + s * kSliceRows + lane;
-    if (row < a.end_row) {
-      const double d = finish_row(a.ep, row, acc);
-      if (d > local_max) local_max = d;
-    }
+    if (row < a.end_row) a.sums[row - a.first_row] = acc;  // epilogue runs as its own elementwise kernel
   }
-  block_max_to_state(local_max, a.state);
 }
+
+#include "sell_stream.cuh"
 
 // ---- heavy rows: one warp per fixed-size edge segment, then one warp per row ------------------------
 
@@ -207,6 +340,7 @@ struct HeavyArgs {
   uint64_t n_heavy;
   uint32_t segment_edges;
   const double *contrib_in;
+  GatherWindow window;
   IterState *state;
   RowEpilogue ep;
 };
@@ -217,6 +351,7 @@ __global__ void __launch_bounds__(kBlockThreads) heavy_segments_kernel(const Hea
   const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * kWarpsPerBlock;
   const uint64_t warp0 = static_cast<uint64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   const uint64_t pol = make_evict_first_policy();
+  const uint64_t gpol = make_gather_policy(a.contrib_in, a.window);
   for (uint64_t g = warp0; g < a.n_seg; g += warps_total) {
     const uint32_t r = a.seg_row[g];
     const uint64_t e0 = a.seg_begin[g];
@@ -230,11 +365,11 @@ __global__ void __launch_bounds__(kBlockThreads) heavy_segments_kernel(const Hea
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) src[j] = ld_index(a.heavy_idx + e + 32ull * j, pol);
 #pragma unroll
-      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib(a.contrib_in + src[j]);
+      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib(a.contrib_in + src[j], gpol);
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) acc += v[j];
     }
-    for (; e < e1; e += 32) acc += ld_contrib(a.contrib_in + ld_index(a.heavy_idx + e, pol));
+    for (; e < e1; e += 32) acc += ld_contrib(a.contrib_in + ld_index(a.heavy_idx + e, pol), gpol);
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(kFull, acc, o);  // fixed tree
     if (lane == 0) a.seg_partial[g] = acc;
   }
@@ -246,13 +381,14 @@ __global__ void __launch_bounds__(kBlockThreads) heavy_finish_kernel(const Heavy
   const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * kWarpsPerBlock;
   const uint64_t warp0 = static_cast<uint64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   double local_max = 0.0;
+  const uint64_t pol = make_evict_first_policy();
   for (uint64_t r = warp0; r < a.n_heavy; r += warps_total) {
     const uint64_t s0 = a.seg_first[r], s1 = a.seg_first[r + 1];
     double acc = 0.0;
     for (uint64_t s = s0 + lane; s < s1; s += 32) acc += a.seg_partial[s];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(kFull, acc, o);
     if (lane == 0) {
-      const double d = finish_row(a.ep, r, acc);
+      const double d = finish_row(a.ep, r, acc, pol);
       if (d > local_max) local_max = d;
     }
   }
@@ -265,10 +401,11 @@ __global__ void __launch_bounds__(kBlockThreads) zero_rows_kernel(uint64_t first
                                                                   IterState *state, const RowEpilogue ep) {
   if (ld_volatile_int(&state->done)) return;
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const uint64_t pol = make_evict_first_policy();
   double local_max = 0.0;
   for (uint64_t r = first_row + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < end_row;
        r += stride) {
-    const double d = finish_row(ep, r, 0.0);
+    const double d = finish_row(ep, r, 0.0, pol);
     if (d > local_max) local_max = d;
   }
   block_max_to_state(local_max, state);
@@ -459,6 +596,31 @@ RowEpilogue make_epilogue(const Graph &g, uint64_t it, const IterateConfig &cfg)
   return ep;
 }
 
+GatherWindow make_window(const Graph &g) {
+  static long hot_mb = -1;
+  if (hot_mb < 0) {
+    const char *s = getenv("MGB200_L2_HOT_MB");
+    hot_mb = s ? strtol(s, nullptr, 10) : 64;  // effective L2 capacity for random gathers on B200 (l2_bench)
+    if (hot_mb < 0) hot_mb = 0;
+  }
+  const uint64_t total = std::min<uint64_t>((g.n + 1) * sizeof(double), 0xFFFFFF00ull);
+  GatherWindow w{};
+  w.total_bytes = static_cast<uint32_t>(total);
+  w.hot_bytes = static_cast<uint32_t>(std::min<uint64_t>(total, static_cast<uint64_t>(hot_mb) << 20));
+  return w;
+}
+
+bool use_stream_kernel() {
+  static int cached = -1;
+  if (cached < 0) {
+    // "rows" (default): warp-per-slice loop, gathers through LDG; "stream": TMA index ring + LDGSTS gathers
+    // (sell_stream.cuh) -- correct, but measured slower (3.4 vs 2.4 ms at scale-26, profiles/r01_stream_vs_rows.md)
+    const char *s = getenv("MGB200_SELL_KERNEL");
+    cached = (s && strcmp(s, "stream") == 0) ? 1 : 0;
+  }
+  return cached == 1;
+}
+
 unsigned long long barrier_timeout_ns() {
   static unsigned long long cached = 0;
   if (!cached) {
@@ -527,6 +689,7 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     h.n_heavy = g.n_heavy;
     h.segment_edges = g.segment_edges;
     h.contrib_in = contrib_in;
+    h.window = make_window(g);
     h.state = g.state;
     h.ep = ep;
     int grid = static_cast<int>(
@@ -546,19 +709,47 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     s.first_row = g.n_heavy;
     s.end_row = g.n_heavy + g.n_sell;
     s.contrib_in = contrib_in;
+    s.window = make_window(g);
     s.state = g.state;
-    s.ep = ep;
+    s.sums = g.sell_sums;
     const int grid = static_cast<int>(
         std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_rows_kernel))),
             ceil_div(g.n_slices, kWarpsPerBlock)));
     const bool timed = g.time_spmv && g.timed_launches < Graph::kMaxTimedLaunches;
     if (timed) MGB_CUDA(cudaEventRecord(g.kev[2 * g.timed_launches], g.stream));
+    if (use_stream_kernel() && g.sell_items > 0) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        MGB_CUDA(cudaFuncSetAttribute(sell_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kStreamSmemBytes));
+        attr_set = true;
+      }
+      SellStreamArgs t{};
+      t.colbase = g.sell_colbase;
+      t.idx = g.sell_idx;
+      t.item_begin = g.sell_item_begin;
+      t.n_items = g.sell_items;
+      t.first_row = s.first_row;
+      t.end_row = s.end_row;
+      t.contrib_in = contrib_in;
+      t.window = s.window;
+      t.state = g.state;
+      t.sums = g.sell_sums;
+      const int sgrid = static_cast<int>(std::min<uint64_t>(g.sm_count, ceil_div(g.sell_items, kStreamWarps)));
+      sell_stream_kernel<<<sgrid, kStreamThreads, kStreamSmemBytes, g.stream>>>(t);
+    } else
     sell_rows_kernel<<<grid, kBlockThreads, 0, g.stream>>>(s);
     if (timed) {
       MGB_CUDA(cudaEventRecord(g.kev[2 * g.timed_launches + 1], g.stream));
       ++g.timed_launches;
     }
-    ++launches;
+    {
+      const int egrid = static_cast<int>(
+          std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_epilogue_kernel))),
+                   ceil_div(g.n_sell, kBlockThreads)));
+      sell_epilogue_kernel<<<egrid, kBlockThreads, 0, g.stream>>>(s.first_row, s.end_row, g.sell_sums, g.state, ep);
+    }
+    launches += 2;
     if (spmv_count) *spmv_count += 1;
   }
   IterEndArgs e{};

@@ -83,14 +83,10 @@ def test_vanished_vertex_analytical_vs_transactional(module):
     gids = np.arange(1, 9, dtype=np.int64)
     src, dst = gids[:-1], gids[1:]
     with fh.Graph(gids, src, dst, transactional=False) as g:
-        full_nodes, full_ranks = module.call(g)
-        g.hide_vertex(4)  # FindVertex fails at emission time
-    # hidden vertices also refuse out-edge iteration, so build a graph where only emission is affected
-    with fh.Graph(gids, src[src != 4], dst[src != 4], transactional=False) as g:
-        g.hide_vertex(8)  # 8 has no out-edges: ingest is unaffected, emission skips the row
+        g.hide_vertex(8)  # FindVertex fails at emission time: analytical mode skips the row
         nodes, ranks = module.call(g)
         assert 8 not in nodes and len(nodes) == len(gids) - 1
-    with fh.Graph(gids, src[src != 4], dst[src != 4], transactional=True) as g:
+    with fh.Graph(gids, src, dst, transactional=True) as g:
         g.hide_vertex(8)
         with pytest.raises(fh.ProcedureError, match=r"^pagerank\.get: Invalid ID!$"):
             module.call(g)
