@@ -155,6 +155,52 @@ class PageRankGraph:
         return out, _stats(st)
 
 
+    # ---- multi-GPU: one partition per GPU (mgb200_pagerank.h "multi-GPU" section) ----------------------
+
+    def export_window(self):
+        """CUDA IPC handle (64 bytes) of this partition's exchange window, for a peer PROCESS."""
+        buf = ctypes.create_string_buffer(N.IPC_HANDLE_BYTES)
+        _check(N.lib().mgb200_graph_export_window(self._h, buf))
+        return buf.raw
+
+    def connect_peers(self, ipc_handles=None, local_graphs=None):
+        """Wire this partition to its peers: ``ipc_handles[q]`` = bytes from peer process q, or
+        ``local_graphs[q]`` = a PageRankGraph of the same process (entry for the own rank is ignored)."""
+        world = self.info["part_world"]
+        harr = (N.vp * world)()
+        garr = (N.vp * world)()
+        keep = []
+        for q in range(world):
+            if q == self.info["part_rank"]:
+                continue
+            if local_graphs is not None and local_graphs[q] is not None:
+                garr[q] = local_graphs[q].handle
+            elif ipc_handles is not None and ipc_handles[q] is not None:
+                b = ctypes.create_string_buffer(bytes(ipc_handles[q]), N.IPC_HANDLE_BYTES)
+                keep.append(b)
+                harr[q] = ctypes.cast(b, N.vp)
+        _check(N.lib().mgb200_graph_connect_peers(self._h, harr, garr))
+
+    def run_partition(self, max_iterations=100, damping_factor=0.85, stop_epsilon=1e-5, time_spmv_kernel=False,
+                      out_device_ptr=None):
+        """Every partition calls this concurrently.  Returns (ranks, vertices, RunStats) for the rows this
+        partition owns: normalised ranks and the ORIGINAL vertex id of each (None, None when
+        ``out_device_ptr`` receives the ranks on the device)."""
+        p, _cb = make_params(max_iterations, damping_factor, stop_epsilon, out_device_ptr is not None,
+                             time_spmv_kernel)
+        st = N.RunStatsC()
+        rows = self.info["local_rows"]
+        if out_device_ptr is not None:
+            _check(N.lib().mgb200_pagerank_run_partition(self._h, ctypes.byref(p), out_device_ptr, None,
+                                                         ctypes.byref(st)))
+            return None, None, _stats(st)
+        ranks = np.empty(rows, dtype=np.float64)
+        verts = np.empty(rows, dtype=np.uint32)
+        _check(N.lib().mgb200_pagerank_run_partition(self._h, ctypes.byref(p), ranks.ctypes.data if rows else None,
+                                                     verts.ctypes.data if rows else None, ctypes.byref(st)))
+        return ranks, verts, _stats(st)
+
+
 def parallel_iterative_pagerank(graph, max_iterations=100, damping_factor=0.85, stop_epsilon=1e-5,
                                 number_of_threads=1):
     """pagerank_alg::ParallelIterativePageRank (pagerank.hpp:107-109).  ``number_of_threads`` is kept

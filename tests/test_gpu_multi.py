@@ -1,0 +1,80 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise): the vertex-partitioned path.  Partitions live in ONE
+process here (peer access between devices, one host thread per GPU, like the query module would drive
+them); bench.py --gpus N exercises the one-process-per-GPU / CUDA-IPC variant of the same kernels."""
+import threading
+
+import numpy as np
+import pytest
+
+from _checkers import Oracle
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-9  # north_star: 1e-6
+
+
+def _device_count():
+    try:
+        import memgraph_b200 as mg
+        return mg.device_count()
+    except Exception:
+        return 0
+
+
+def run_partitioned(mg, n, f, t, world, **kw):
+    graphs = [mg.PageRankGraph.from_arrays(n, f, t, device=q, part_rank=q, part_world=world) for q in range(world)]
+    for g in graphs:
+        g.connect_peers(local_graphs=graphs)
+    results = [None] * world
+    errors = []
+
+    def work(q):
+        try:
+            results[q] = graphs[q].run_partition(**kw)
+        except Exception as e:  # pragma: no cover
+            errors.append((q, e))
+
+    threads = [threading.Thread(target=work, args=(q,)) for q in range(world)]
+    [th.start() for th in threads]
+    [th.join() for th in threads]
+    infos = [dict(g.info) for g in graphs]
+    for g in graphs:
+        g.close()
+    assert not errors, errors
+    out = np.full(n, np.nan)
+    for ranks, verts, _ in results:
+        out[verts.astype(np.int64)] = ranks
+    return out, results, infos
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_partitioned_equals_oracle(world):
+    if _device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import memgraph_b200 as mg
+    oracle = Oracle()
+    scale = 16
+    n, m = 1 << scale, 16 << scale
+    f, t = mg.rmat_edges_host(scale, m)
+    for kw in [dict(max_iterations=20, damping_factor=0.85, stop_epsilon=0.0), dict()]:
+        got, results, infos = run_partitioned(mg, n, f, t, world, **kw)
+        ref, it = oracle.pagerank(n, f, t, **kw)
+        assert not np.isnan(got).any()
+        assert all(st.iterations == it for _, _, st in results)  # every partition stops at the same iteration
+        assert float(np.max(np.abs(got - ref) / ref)) < REL_TOL
+        assert sum(i["local_rows"] for i in infos) == n and sum(i["local_edges"] for i in infos) == m
+        edges = [i["local_edges"] for i in infos]
+        assert max(edges) < 1.25 * (m / world) + 70000  # dealt round-robin by degree rank: edge-balanced
+
+
+def test_partitioned_matches_single_gpu_bitwise_sum():
+    if _device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import memgraph_b200 as mg
+    scale = 18
+    n, m = 1 << scale, 16 << scale
+    f, t = mg.rmat_edges_host(scale, m)
+    with mg.PageRankGraph.from_arrays(n, f, t) as g:
+        single, st1 = g.run(max_iterations=20, stop_epsilon=0.0)
+    multi, results, _ = run_partitioned(mg, n, f, t, 2, max_iterations=20, stop_epsilon=0.0)
+    assert float(np.max(np.abs(multi - single) / single)) < 1e-12
+    assert abs(multi.sum() - 1.0) < 1e-12
