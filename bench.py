@@ -38,6 +38,7 @@ EDGE_FACTOR = 16
 SEED = 42
 ALGO_BYTES_PER_EDGE = 12  # 4 B column index + 8 B gathered FP64 contribution      
 ALGO_BYTES_PER_ROW = 24   # 4 B row offset + 4 B out-degree + 8 B old + 8 B new rank
+REAL_STDOUT = 1
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -169,7 +170,7 @@ def run_reference_arm(args):
         "e2e": {"value": res["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -181,6 +182,15 @@ def dev_alloc(N, lib, device, nbytes):
     if rc:
         raise RuntimeError(lib.mgb200_last_error().decode())
     return p
+
+
+CLASS_NAMES = ["zero_rows", "sell_rows", "sell_epilogue_push", "heavy_segments", "heavy_finish", "iter_end_barrier"]
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, torchrun chatter from
+    libraries writing to fd 1) was diverted to stderr by main()."""
+    os.write(REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
 def run_b200_arm(args):
@@ -257,6 +267,7 @@ def run_b200_arm(args):
     if rank == 0:
         sampler.start()
     step_ms, launches, kernel_ms, kernel_launches, iters = [], 0, 0.0, 0, 0
+    class_ms = np.zeros(6)
     for _ in range(args.steps):
         if dist is not None:
             dist.barrier()
@@ -265,6 +276,7 @@ def run_b200_arm(args):
         launches += st.kernel_launches
         kernel_ms += st.kernel_ms
         kernel_launches += st.kernel_timed_launches
+        class_ms += np.array(st.class_ms)
         iters = st.iterations
     clocks = sampler.stop() if rank == 0 else None
     total_ms = float(sum(step_ms))
@@ -281,9 +293,14 @@ def run_b200_arm(args):
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "scale": scale, "ms_per_iteration": total_ms / args.steps / ITERATIONS,
-                              "edges_per_s": value, "sell_kernel_ms": kernel_ms / max(kernel_launches, 1),
-                              "tag": os.environ.get("MGB200_TAG", "")}), flush=True)
+            emit({"quick": True, "scale": scale, "n_gpus": world, "ms_per_iteration": total_ms / args.steps / ITERATIONS,
+                  "edges_per_s": value, "sell_kernel_ms": kernel_ms / max(kernel_launches, 1),
+                  "class_ms_per_iteration": {k: round(float(v) / (args.steps * ITERATIONS), 4)
+                                             for k, v in zip(CLASS_NAMES, class_ms)},
+                  "tag": os.environ.get("MGB200_TAG", "")})
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return 0
     # e2e: the public call with a HOST output buffer (D2H of the ranks inside the timed region)
     e2e = None
@@ -373,8 +390,9 @@ def run_b200_arm(args):
                    "sell_entries": info["sell_entries"], "zero_rows": info["zero_rows"]},
         "ms_per_iteration": total_ms / args.steps / ITERATIONS,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "kernel_ms_per_iteration": {k: float(v) / (args.steps * ITERATIONS) for k, v in zip(CLASS_NAMES, class_ms)},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -393,6 +411,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="sweep mode: device-resident timing only, compact JSON")
     args = ap.parse_args()
+    global REAL_STDOUT
+    sys.stdout.flush()
+    REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # anything a library prints to stdout lands on stderr; emit() writes the JSON line
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_b200_arm(args)

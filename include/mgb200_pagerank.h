@@ -73,6 +73,9 @@ typedef struct mgb200_run_stats {
   double kernel_ms;     /* CUDA-event time summed over the timed launches of the dominant (SELL)
                            kernel; 0 unless params.time_spmv_kernel                       */
   uint64_t kernel_timed_launches; /* how many launches kernel_ms covers (first <= 64)    */
+  double class_ms[6];   /* per kernel class, summed over the timed iterations: 0 zero-rows, 1 SELL rows,
+                           2 SELL epilogue (+peer push), 3 heavy segments, 4 heavy finish, 5 iteration end
+                           (barrier + convergence test); classes may overlap in time                 */
   uint64_t kernel_launches; /* kernels launched inside the timed region                 */
   uint64_t spmv_launches;   /* launches of the dominant (SELL) kernel                    */
 } mgb200_run_stats;

@@ -22,7 +22,7 @@ class GraphInfo(ctypes.Structure):
 
 class RunStatsC(ctypes.Structure):
     _fields_ = [("iterations", u64), ("last_diff", f64), ("rank_sum", f64), ("iterate_ms", f64), ("kernel_ms", f64),
-                ("kernel_timed_launches", u64), ("kernel_launches", u64), ("spmv_launches", u64)]
+                ("kernel_timed_launches", u64), ("class_ms", f64 * 6), ("kernel_launches", u64), ("spmv_launches", u64)]
 
 
 ABORT_FN = ctypes.CFUNCTYPE(ctypes.c_int, vp)

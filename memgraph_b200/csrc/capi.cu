@@ -89,8 +89,13 @@ int iterate(Graph &g, const mgb200_run_params &p, mgb200_run_stats &stats) {
   }
   g.time_spmv = p.time_spmv_kernel != 0;
   g.timed_launches = 0;
-  if (g.time_spmv && !g.kev[0])
-    for (auto &e : g.kev) MGB_CUDA(cudaEventCreate(&e));
+  if (g.time_spmv) {
+    // fresh events every run: a never-recorded event marks "kernel class not launched in that iteration"
+    for (auto &e : g.kev) {
+      if (e) cudaEventDestroy(e);
+      MGB_CUDA(cudaEventCreate(&e));
+    }
+  }
   int rc = launch_init(g);
   if (rc) return rc;
   rc = launch_barrier(g);  // peers have initialised before anyone pushes into their buffers
@@ -138,13 +143,24 @@ int iterate(Graph &g, const mgb200_run_params &p, mgb200_run_stats &stats) {
   stats.kernel_launches = launches;
   // launches past the convergence point return immediately; report the ones that did work
   stats.spmv_launches = std::min<uint64_t>(spmv, stats.iterations);
-  const int timed = static_cast<int>(std::min<uint64_t>(g.timed_launches, stats.spmv_launches));
+  const int timed = static_cast<int>(std::min<uint64_t>(g.timed_launches, stats.iterations));
   for (int i = 0; i < timed; ++i) {
-    float kms = 0.f;
-    MGB_CUDA(cudaEventElapsedTime(&kms, g.kev[2 * i], g.kev[2 * i + 1]));
-    stats.kernel_ms += kms;
+    for (int c = 0; c < Graph::kClasses; ++c) {
+      cudaEvent_t e0 = g.kev[(i * Graph::kClasses + c) * 2], e1 = g.kev[(i * Graph::kClasses + c) * 2 + 1];
+      if (cudaEventQuery(e0) != cudaSuccess || cudaEventQuery(e1) != cudaSuccess) {
+        cudaGetLastError();
+        continue;  // this kernel class was not launched in that iteration
+      }
+      float kms = 0.f;
+      if (cudaEventElapsedTime(&kms, e0, e1) != cudaSuccess) {
+        cudaGetLastError();
+        continue;
+      }
+      stats.class_ms[c] += kms;
+    }
   }
-  stats.kernel_timed_launches = timed;
+  stats.kernel_ms = stats.class_ms[Graph::kClsSell];
+  stats.kernel_timed_launches = g.n_slices > 0 ? timed : 0;
   return MGB200_OK;
 }
 

@@ -102,11 +102,17 @@ struct Graph {
   uint64_t resident_bytes = 0;
   double build_ms = 0.0;
   cudaEvent_t ev[4] = {};
-  // optional per-launch timing of the dominant (SELL) kernel: event pairs around its first launches
+  // side stream for the SELL epilogue (overlaps the peer push with the heavy-row kernels)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  bool overlap_epilogue = true;
+  // optional per-launch timing: an event pair around every kernel of the first kMaxTimedLaunches iterations
   static constexpr int kMaxTimedLaunches = 64;
+  static constexpr int kClasses = 6;
+  enum { kClsZero = 0, kClsSell, kClsSellEpi, kClsHeavySeg, kClsHeavyFin, kClsIterEnd };
   bool time_spmv = false;
-  int timed_launches = 0;
-  cudaEvent_t kev[2 * kMaxTimedLaunches] = {};
+  int timed_launches = 0;  // iterations whose kernels carry event pairs
+  cudaEvent_t kev[2 * kClasses * kMaxTimedLaunches] = {};
 
   double *contrib(int parity) const {
     return reinterpret_cast<double *>(static_cast<char *>(window) + kFlagPageBytes + parity * contrib_stride);

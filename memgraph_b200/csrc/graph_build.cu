@@ -309,6 +309,9 @@ void free_graph(Graph &g) {
     if (e) cudaEventDestroy(e);
   for (auto &e : g.kev)
     if (e) cudaEventDestroy(e);
+  if (g.fork_ev) cudaEventDestroy(g.fork_ev);
+  if (g.join_ev) cudaEventDestroy(g.join_ev);
+  if (g.stream2) cudaStreamDestroy(g.stream2);
   if (g.stream) cudaStreamDestroy(g.stream);
 }
 
@@ -318,6 +321,13 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   MGB_CUDA(cudaGetDeviceProperties(&prop, g.device));
   g.sm_count = prop.multiProcessorCount;
   MGB_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  MGB_CUDA(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
+  MGB_CUDA(cudaEventCreateWithFlags(&g.fork_ev, cudaEventDisableTiming));
+  MGB_CUDA(cudaEventCreateWithFlags(&g.join_ev, cudaEventDisableTiming));
+  {
+    const char *s = getenv("MGB200_OVERLAP_EPILOGUE");
+    g.overlap_epilogue = !(s && s[0] == '0');
+  }
   for (auto &e : g.ev) MGB_CUDA(cudaEventCreate(&e));
   cudaStream_t st = g.stream;
   const uint64_t n = g.n, m = g.m;

@@ -661,46 +661,32 @@ int launch_barrier(Graph &g) {
   return MGB200_OK;
 }
 
-// One iteration = zero rows (iterations 0 and 1 only) + SELL rows + heavy segments + heavy finish
-// + iteration end.  Every kernel returns immediately once state->done is set, so the host may
-// enqueue iterations ahead of the convergence decision.
+// One iteration.  Main stream: zero rows (iterations 0 and 1 only) -> SELL rows -> heavy segments ->
+// heavy finish -> [join] -> iteration end.  Side stream: the SELL epilogue, forked after the SELL rows:
+// it is the kernel that pushes contributions to the peer GPUs (NVLink-bound), so it overlaps with the
+// heavy-row kernels (L2-gather-bound) instead of queueing behind them.  Every kernel returns immediately
+// once state->done is set, so the host may enqueue iterations ahead of the convergence decision.
 int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *launch_count,
                      uint64_t *spmv_count) {
   const RowEpilogue ep = make_epilogue(g, it, cfg);
   const double *contrib_in = g.contrib(static_cast<int>(it & 1ull));
   uint64_t launches = 0;
+  const bool timed = g.time_spmv && g.timed_launches < Graph::kMaxTimedLaunches;
+  auto tick = [&](int cls, int edge, cudaStream_t st) -> cudaError_t {
+    if (!timed) return cudaSuccess;
+    return cudaEventRecord(g.kev[(g.timed_launches * Graph::kClasses + cls) * 2 + edge], st);
+  };
   if (g.n_zero > 0 && it < 2) {
     const uint64_t first = g.n_heavy + g.n_sell;
     const int grid = static_cast<int>(
         std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(zero_rows_kernel))),
-            ceil_div(g.n_zero, kBlockThreads)));
+                 ceil_div(g.n_zero, kBlockThreads)));
+    MGB_CUDA(tick(Graph::kClsZero, 0, g.stream));
     zero_rows_kernel<<<grid, kBlockThreads, 0, g.stream>>>(first, first + g.n_zero, g.state, ep);
+    MGB_CUDA(tick(Graph::kClsZero, 1, g.stream));
     ++launches;
   }
-  if (g.n_seg > 0) {
-    HeavyArgs h{};
-    h.heavy_ptr = g.heavy_ptr;
-    h.heavy_idx = g.heavy_idx;
-    h.seg_row = g.seg_row;
-    h.seg_begin = g.seg_begin;
-    h.seg_first = g.seg_first;
-    h.seg_partial = g.seg_partial;
-    h.n_seg = g.n_seg;
-    h.n_heavy = g.n_heavy;
-    h.segment_edges = g.segment_edges;
-    h.contrib_in = contrib_in;
-    h.window = make_window(g);
-    h.state = g.state;
-    h.ep = ep;
-    int grid = static_cast<int>(
-        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_segments_kernel))),
-            ceil_div(g.n_seg, kWarpsPerBlock)));
-    heavy_segments_kernel<<<grid, kBlockThreads, 0, g.stream>>>(h);
-    grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_finish_kernel))),
-                                ceil_div(g.n_heavy, kWarpsPerBlock)));
-    heavy_finish_kernel<<<grid, kBlockThreads, 0, g.stream>>>(h);
-    launches += 2;
-  }
+  bool forked = false;
   if (g.n_slices > 0) {
     SellArgs s{};
     s.colbase = g.sell_colbase;
@@ -712,11 +698,7 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     s.window = make_window(g);
     s.state = g.state;
     s.sums = g.sell_sums;
-    const int grid = static_cast<int>(
-        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_rows_kernel))),
-            ceil_div(g.n_slices, kWarpsPerBlock)));
-    const bool timed = g.time_spmv && g.timed_launches < Graph::kMaxTimedLaunches;
-    if (timed) MGB_CUDA(cudaEventRecord(g.kev[2 * g.timed_launches], g.stream));
+    MGB_CUDA(tick(Graph::kClsSell, 0, g.stream));
     if (use_stream_kernel() && g.sell_items > 0) {
       static bool attr_set = false;
       if (!attr_set) {
@@ -737,28 +719,70 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
       t.sums = g.sell_sums;
       const int sgrid = static_cast<int>(std::min<uint64_t>(g.sm_count, ceil_div(g.sell_items, kStreamWarps)));
       sell_stream_kernel<<<sgrid, kStreamThreads, kStreamSmemBytes, g.stream>>>(t);
-    } else
-    sell_rows_kernel<<<grid, kBlockThreads, 0, g.stream>>>(s);
-    if (timed) {
-      MGB_CUDA(cudaEventRecord(g.kev[2 * g.timed_launches + 1], g.stream));
-      ++g.timed_launches;
+    } else {
+      const int grid = static_cast<int>(
+          std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_rows_kernel))),
+                   ceil_div(g.n_slices, kWarpsPerBlock)));
+      sell_rows_kernel<<<grid, kBlockThreads, 0, g.stream>>>(s);
     }
-    {
-      const int egrid = static_cast<int>(
-          std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_epilogue_kernel))),
-                   ceil_div(g.n_sell, kBlockThreads)));
-      sell_epilogue_kernel<<<egrid, kBlockThreads, 0, g.stream>>>(s.first_row, s.end_row, g.sell_sums, g.state, ep);
+    MGB_CUDA(tick(Graph::kClsSell, 1, g.stream));
+    // fork: epilogue on the side stream
+    cudaStream_t es = g.overlap_epilogue ? g.stream2 : g.stream;
+    if (g.overlap_epilogue) {
+      MGB_CUDA(cudaEventRecord(g.fork_ev, g.stream));
+      MGB_CUDA(cudaStreamWaitEvent(g.stream2, g.fork_ev, 0));
+      forked = true;
     }
+    const int egrid = static_cast<int>(
+        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_epilogue_kernel))),
+                 ceil_div(g.n_sell, kBlockThreads)));
+    MGB_CUDA(tick(Graph::kClsSellEpi, 0, es));
+    sell_epilogue_kernel<<<egrid, kBlockThreads, 0, es>>>(s.first_row, s.end_row, g.sell_sums, g.state, ep);
+    MGB_CUDA(tick(Graph::kClsSellEpi, 1, es));
+    if (forked) MGB_CUDA(cudaEventRecord(g.join_ev, g.stream2));
     launches += 2;
     if (spmv_count) *spmv_count += 1;
   }
+  if (g.n_seg > 0) {
+    HeavyArgs h{};
+    h.heavy_ptr = g.heavy_ptr;
+    h.heavy_idx = g.heavy_idx;
+    h.seg_row = g.seg_row;
+    h.seg_begin = g.seg_begin;
+    h.seg_first = g.seg_first;
+    h.seg_partial = g.seg_partial;
+    h.n_seg = g.n_seg;
+    h.n_heavy = g.n_heavy;
+    h.segment_edges = g.segment_edges;
+    h.contrib_in = contrib_in;
+    h.window = make_window(g);
+    h.state = g.state;
+    h.ep = ep;
+    int grid = static_cast<int>(
+        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_segments_kernel))),
+                 ceil_div(g.n_seg, kWarpsPerBlock)));
+    MGB_CUDA(tick(Graph::kClsHeavySeg, 0, g.stream));
+    heavy_segments_kernel<<<grid, kBlockThreads, 0, g.stream>>>(h);
+    MGB_CUDA(tick(Graph::kClsHeavySeg, 1, g.stream));
+    grid = static_cast<int>(
+        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_finish_kernel))),
+                 ceil_div(g.n_heavy, kWarpsPerBlock)));
+    MGB_CUDA(tick(Graph::kClsHeavyFin, 0, g.stream));
+    heavy_finish_kernel<<<grid, kBlockThreads, 0, g.stream>>>(h);
+    MGB_CUDA(tick(Graph::kClsHeavyFin, 1, g.stream));
+    launches += 2;
+  }
+  if (forked) MGB_CUDA(cudaStreamWaitEvent(g.stream, g.join_ev, 0));
   IterEndArgs e{};
   e.bar = make_barrier(g);
   e.max_iterations = cfg.max_iterations;
   e.eps = cfg.eps;
+  MGB_CUDA(tick(Graph::kClsIterEnd, 0, g.stream));
   iter_end_kernel<<<1, 32, 0, g.stream>>>(e);
+  MGB_CUDA(tick(Graph::kClsIterEnd, 1, g.stream));
   ++launches;
   MGB_CUDA(cudaGetLastError());
+  if (timed) ++g.timed_launches;
   if (launch_count) *launch_count += launches;
   return MGB200_OK;
 }

@@ -32,13 +32,14 @@ class RunStats:
     iterate_ms: float
     kernel_ms: float
     kernel_timed_launches: int
+    class_ms: tuple
     kernel_launches: int
     spmv_launches: int
 
 
 def _stats(c):
     return RunStats(c.iterations, c.last_diff, c.rank_sum, c.iterate_ms, c.kernel_ms, c.kernel_timed_launches,
-                    c.kernel_launches, c.spmv_launches)
+                    tuple(c.class_ms), c.kernel_launches, c.spmv_launches)
 
 
 def make_params(max_iterations, damping_factor, stop_epsilon, on_device=False, time_spmv_kernel=False,
