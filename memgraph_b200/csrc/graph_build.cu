@@ -350,7 +350,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   g.window_bytes = kFlagPageBytes + 2 * g.contrib_stride;
   MGB_CUDA(cudaMalloc(&g.window, g.window_bytes));
   g.resident_bytes += g.window_bytes;
-  MGB_CUDA(cudaMemsetAsync(g.window, 0, kFlagPageBytes, st));
+  MGB_CUDA(cudaMemsetAsync(g.window, 0, g.window_bytes, st));
   for (int q = 0; q < kMaxPeers; ++q) {
     g.peers.contrib[0][q] = g.peers.contrib[1][q] = nullptr;
     g.peers.flags[q] = nullptr;
@@ -472,6 +472,14 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   if (g.n_heavy) {
     MGB_CUDA(cudaMemcpyAsync(&g.heavy_edges, row_ptr + g.n_heavy, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     MGB_CUDA(cudaStreamSynchronize(st));
+    if (!getenv("MGB200_SEGMENT_EDGES")) {
+      // one warp per segment: aim for >= 8 segments per resident warp (64 warps/SM) so the tail is short
+      // when a partition holds few heavy edges (multi-GPU), capped at 4096 edges
+      const uint64_t resident_warps = static_cast<uint64_t>(g.sm_count) * 64;
+      uint64_t seg = g.heavy_edges / (resident_warps * 8);
+      seg = (seg / 256) * 256;
+      g.segment_edges = static_cast<uint32_t>(std::min<uint64_t>(4096, std::max<uint64_t>(256, seg)));
+    }
     MGB_CUDA(keep_alloc(g, &g.heavy_ptr, g.n_heavy + 1));
     MGB_CUDA(cudaMemcpyAsync(g.heavy_ptr, row_ptr, (g.n_heavy + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     MGB_CUDA(keep_alloc(g, &g.heavy_idx, g.heavy_edges));

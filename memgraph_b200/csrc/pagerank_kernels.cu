@@ -150,10 +150,15 @@ __device__ __forceinline__ double finish_row(const RowEpilogue &ep, uint64_t loc
   st_stream_f64(ep.rank + local_row, next, stream_pol);
   const uint64_t label = ep.row_lo + local_row;
   const uint32_t od = ld_index(ep.outdeg + label, stream_pol);
-  const double c = od ? __ddiv_rn(next, static_cast<double>(od)) : 0.0;  // :93 quotient, once per vertex
+  // A vertex without out-edges is never a gather source, so its contribution is never read: no division,
+  // no store, and -- what matters across GPUs -- no NVLink push.  Labels are sorted by (in-degree, out-degree)
+  // descending, so these vertices are the contiguous tail of every in-degree class: whole warps skip.
+  if (od != 0) {
+    const double c = __ddiv_rn(next, static_cast<double>(od));  // :93 quotient, once per vertex
 #pragma unroll
-  for (int q = 0; q < kMaxPeers; ++q) {
-    if (q < ep.world) st_stream_f64(ep.contrib_out[q] + label, c, stream_pol);  // q != self: NVLink store
+    for (int q = 0; q < kMaxPeers; ++q) {
+      if (q < ep.world) st_stream_f64(ep.contrib_out[q] + label, c, stream_pol);  // q != self: NVLink store
+    }
   }
   return fabs(next - prev);
 }
@@ -252,18 +257,26 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_
   const uint64_t gpol = make_gather_policy(a.contrib_in, a.window);
   const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * kWarpsPerBlock;
   const uint64_t warp0 = static_cast<uint64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  // Slices are sorted by width (descending), so a plain warp-strided walk gives warp 0 up to one full
+  // slice-width more columns than the last warp in EVERY pass; alternating the direction of the walk
+  // each pass (boustrophedon) cancels that skew pairwise.
+  auto slice_of = [&](uint64_t pass) -> uint64_t {
+    return pass * warps_total + ((pass & 1ull) ? (warps_total - 1 - warp0) : warp0);
+  };
   uint64_t c0 = 0, c1 = 0;
-  if (warp0 < a.n_slices) {
-    c0 = a.colbase[warp0];
-    c1 = a.colbase[warp0 + 1];
+  if (slice_of(0) < a.n_slices) {
+    c0 = a.colbase[slice_of(0)];
+    c1 = a.colbase[slice_of(0) + 1];
   }
-  for (uint64_t s = warp0; s < a.n_slices; s += warps_total) {
+  for (uint64_t pass = 0; pass * warps_total < a.n_slices; ++pass) {
+    const uint64_t s = slice_of(pass);
+    if (s >= a.n_slices) continue;  // only in the last, partial pass
     const uint32_t width = static_cast<uint32_t>(c1 - c0);
     const uint32_t *p = a.idx + c0 * kSliceRows + lane;
     const uint64_t cbase = c0;
     (void)cbase;
     // slice descriptor of this warp's NEXT slice: issued now, consumed after this slice's gathers
-    const uint64_t s_next = s + warps_total;
+    const uint64_t s_next = slice_of(pass + 1);
     if (s_next < a.n_slices) {
       c0 = a.colbase[s_next];
       c1 = a.colbase[s_next + 1];
