@@ -127,6 +127,13 @@ int mgb200_parallel_iterative_pagerank(uint64_t n, uint64_t m, const uint64_t *f
                                        uint64_t max_iterations, double damping_factor, double stop_epsilon,
                                        uint32_t number_of_threads, double *rank_out, uint64_t *iterations_out);
 
+/* Same call spread over `gpu_count` GPUs of this machine (devices[q], or ordinals 0..gpu_count-1 when
+ * NULL): one partition and one host thread per GPU inside the call, peers wired by peer access. */
+int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
+                                             uint64_t max_iterations, double damping_factor, double stop_epsilon,
+                                             uint32_t number_of_threads, uint32_t gpu_count, const int *devices,
+                                             double *rank_out, uint64_t *iterations_out);
+
 /* ---- multi-GPU: one partition per GPU, contributions pushed to peers over NVLink --------------- */
 
 #define MGB200_IPC_HANDLE_BYTES 64

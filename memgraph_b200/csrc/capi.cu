@@ -11,6 +11,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "core.hpp"
 #include "rmat.hpp"
@@ -96,11 +98,11 @@ int iterate(Graph &g, const mgb200_run_params &p, mgb200_run_stats &stats) {
       MGB_CUDA(cudaEventCreate(&e));
     }
   }
-  int rc = launch_init(g);
+  MGB_CUDA(cudaEventRecord(g.ev[2], g.stream));  // timed region starts with the rank = 1/N initialisation (:199)
+  int rc = launch_init(g, cfg);
   if (rc) return rc;
   rc = launch_barrier(g);  // peers have initialised before anyone pushes into their buffers
   if (rc) return rc;
-  MGB_CUDA(cudaEventRecord(g.ev[2], g.stream));
   uint64_t launches = 0, spmv = 0;
   uint64_t it = 0;
   bool done = p.max_iterations == 0;
@@ -411,6 +413,79 @@ int mgb200_parallel_iterative_pagerank(uint64_t n, uint64_t m, const uint64_t *f
   mgb200_graph_destroy(g);
   if (rc) return rc;
   if (iterations_out) *iterations_out = stats.iterations;
+  return MGB200_OK;
+}
+
+int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
+                                             uint64_t max_iterations, double damping_factor, double stop_epsilon,
+                                             uint32_t number_of_threads, uint32_t gpu_count, const int *devices,
+                                             double *rank_out, uint64_t *iterations_out) {
+  if (gpu_count <= 1) {
+    return mgb200_parallel_iterative_pagerank(n, m, from, to, max_iterations, damping_factor, stop_epsilon,
+                                              number_of_threads, rank_out, iterations_out);
+  }
+  if (number_of_threads == 0) {
+    set_error(MGB200_MSG_ZERO_THREADS);
+    return MGB200_ERR_ZERO_THREADS;
+  }
+  if (gpu_count > static_cast<uint32_t>(kMaxPeers)) {
+    set_error("at most " + std::to_string(kMaxPeers) + " GPUs per graph");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  if (n == 0) {
+    return mgb200_parallel_iterative_pagerank(n, m, from, to, max_iterations, damping_factor, stop_epsilon,
+                                              number_of_threads, rank_out, iterations_out);
+  }
+  std::vector<mgb200_graph *> parts(gpu_count, nullptr);
+  auto destroy_all = [&]() {
+    for (auto *p : parts) mgb200_graph_destroy(p);
+  };
+  for (uint32_t q = 0; q < gpu_count; ++q) {
+    const int dev = devices ? devices[q] : static_cast<int>(q);
+    const int rc = mgb200_graph_create_host(dev, n, m, from, to, q, gpu_count, &parts[q]);
+    if (rc) {
+      destroy_all();
+      return rc;
+    }
+  }
+  for (uint32_t q = 0; q < gpu_count; ++q) {
+    const int rc = mgb200_graph_connect_peers(parts[q], nullptr, parts.data());
+    if (rc) {
+      destroy_all();
+      return rc;
+    }
+  }
+  // one host thread per GPU: the partitions meet in device-side barriers, so they must all be launched
+  std::vector<int> rcs(gpu_count, MGB200_OK);
+  std::vector<std::string> messages(gpu_count);
+  std::vector<std::vector<double>> ranks(gpu_count);
+  std::vector<std::vector<uint32_t>> vertices(gpu_count);
+  std::vector<mgb200_run_stats> stats(gpu_count);
+  std::vector<std::thread> workers;
+  for (uint32_t q = 0; q < gpu_count; ++q) {
+    workers.emplace_back([&, q]() {
+      mgb200_run_params p{};
+      p.max_iterations = max_iterations;
+      p.damping_factor = damping_factor;
+      p.stop_epsilon = stop_epsilon;
+      const uint64_t rows = parts[q]->g.local_rows;
+      ranks[q].resize(rows);
+      vertices[q].resize(rows);
+      rcs[q] = mgb200_pagerank_run_partition(parts[q], &p, ranks[q].data(), vertices[q].data(), &stats[q]);
+      if (rcs[q]) messages[q] = mgb200_last_error();
+    });
+  }
+  for (auto &w : workers) w.join();
+  destroy_all();
+  for (uint32_t q = 0; q < gpu_count; ++q) {
+    if (rcs[q]) {
+      set_error(messages[q]);
+      return rcs[q];
+    }
+  }
+  for (uint32_t q = 0; q < gpu_count; ++q)
+    for (size_t r = 0; r < ranks[q].size(); ++r) rank_out[vertices[q][r]] = ranks[q][r];
+  if (iterations_out) *iterations_out = stats[0].iterations;
   return MGB200_OK;
 }
 

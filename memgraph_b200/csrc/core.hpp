@@ -62,6 +62,8 @@ struct Graph {
   uint64_t local_edges = 0;
   uint64_t n_heavy = 0, n_sell = 0, n_zero = 0;
   uint32_t heavy_min_degree = 0, segment_edges = 0;
+  uint64_t zero_lo[kMaxPeers] = {}, zero_hi[kMaxPeers] = {};  // global label range of every partition's zero rows
+  bool any_zero_rows = false;
 
   // label-space metadata
   uint32_t *label_of = nullptr;     // [n]  original id -> global label
@@ -142,7 +144,7 @@ struct IterateConfig {
   double eps;
 };
 constexpr int kSumBlocks = 1024;
-int launch_init(Graph &g);
+int launch_init(Graph &g, const IterateConfig &cfg);
 int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *launch_count, uint64_t *spmv_count);
 int launch_barrier(Graph &g);
 int launch_sum_and_exchange(Graph &g);

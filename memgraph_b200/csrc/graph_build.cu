@@ -137,6 +137,19 @@ __global__ void class_count_kernel(uint64_t rows, const uint32_t *indeg_local, u
   }
 }
 
+// non-zero in-degree rows per partition: label l belongs to the partition whose [start, start+count) holds it
+__global__ void nonzero_per_partition_kernel(Dealer deal, const uint32_t *indeg_l, unsigned long long *nz) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint32_t q = 0; q < deal.world; ++q) {
+    const uint64_t lo = deal.start(q), hi = lo + deal.count(q);
+    unsigned long long c = 0;
+    for (uint64_t l = lo + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; l < hi; l += stride)
+      c += indeg_l[l] > 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(nz + q, c);
+  }
+}
+
 struct U32ToU64 {
   __host__ __device__ uint64_t operator()(uint32_t v) const { return v; }
 };
@@ -426,6 +439,21 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   unsigned long long counts_host[4] = {0, 0, 0, 0};
   MGB_CUDA(cudaMemcpyAsync(counts_host, counts, sizeof(counts_host), cudaMemcpyDeviceToHost, st));
   MGB_CUDA(cudaStreamSynchronize(st));
+  {
+    unsigned long long *nz = nullptr;
+    MGB_CUDA(tmp.alloc(&nz, kMaxPeers));
+    MGB_CUDA(cudaMemsetAsync(nz, 0, kMaxPeers * sizeof(unsigned long long), st));
+    nonzero_per_partition_kernel<<<blocks_for(n / g.part_world + 1, g.sm_count), kThreads, 0, st>>>(deal, indeg_l, nz);
+    unsigned long long nz_host[kMaxPeers] = {};
+    MGB_CUDA(cudaMemcpyAsync(nz_host, nz, sizeof(nz_host), cudaMemcpyDeviceToHost, st));
+    MGB_CUDA(cudaStreamSynchronize(st));
+    g.any_zero_rows = false;
+    for (uint32_t q = 0; q < g.part_world; ++q) {
+      g.zero_lo[q] = deal.start(q) + nz_host[q];
+      g.zero_hi[q] = deal.start(q) + deal.count(q);
+      if (g.zero_hi[q] > g.zero_lo[q]) g.any_zero_rows = true;
+    }
+  }
   g.n_heavy = counts_host[0];
   g.n_sell = counts_host[1] - counts_host[0];
   g.n_zero = g.local_rows - counts_host[1];

@@ -183,19 +183,40 @@ __device__ __forceinline__ void block_max_to_state(double local_max, IterState *
 
 // ---- init -------------------------------------------------------------------------------------------
 
+// Zero in-degree rows never receive anything: their rank is (1-d)/N after the first iteration and stays
+// there, and their contribution is (that rank)/outdeg.  Every partition knows every partition's zero-row
+// label ranges (graph_build.cu), so all of it is set up locally -- no kernel in the iteration loop, no
+// NVLink traffic: init writes rank = (1-d)/N for the own zero rows, contrib[0] = (1/N)/outdeg for every
+// label and contrib[1] = ((1-d)/N)/outdeg for all zero-row labels; zero_refresh_kernel rewrites contrib[0]
+// for the zero-row labels during iteration 1.  Their one-time delta |(1-d)/N - 1/N| enters iteration 0's
+// L-infinity test through iter_end_kernel (extra_diff_bits).
+struct ZeroRanges {
+  uint64_t lo[kMaxPeers];
+  uint64_t hi[kMaxPeers];
+  int world;
+};
+
 // rank = 1/N (:199); contrib[0] = (1/N)/outdeg for EVERY label (each partition fills its own full
 // copy, so iteration 0 needs no exchange); pad slots = 0.
-__global__ void __launch_bounds__(kBlockThreads) init_kernel(uint64_t n, uint64_t local_rows, double *rank,
-                                                             const uint32_t *outdeg, double *contrib0,
-                                                             double *contrib1, IterState *state) {
+__global__ void __launch_bounds__(kBlockThreads) init_kernel(uint64_t n, uint64_t local_rows, uint64_t local_nonzero,
+                                                             double zero_rank, double *rank, const uint32_t *outdeg,
+                                                             double *contrib0, double *contrib1, ZeroRanges zr,
+                                                             IterState *state) {
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const double r0 = 1.0 / static_cast<double>(n);
   for (uint64_t i = tid; i < n; i += stride) {
     const uint32_t od = outdeg[i];
-    contrib0[i] = od ? __ddiv_rn(r0, static_cast<double>(od)) : 0.0;
+    if (od) contrib0[i] = __ddiv_rn(r0, static_cast<double>(od));
   }
-  for (uint64_t i = tid; i < local_rows; i += stride) rank[i] = r0;
+  for (int q = 0; q < kMaxPeers; ++q) {
+    if (q >= zr.world) break;
+    for (uint64_t i = zr.lo[q] + tid; i < zr.hi[q]; i += stride) {
+      const uint32_t od = outdeg[i];
+      if (od) contrib1[i] = __ddiv_rn(zero_rank, static_cast<double>(od));
+    }
+  }
+  for (uint64_t i = tid; i < local_rows; i += stride) rank[i] = i < local_nonzero ? r0 : zero_rank;
   if (tid == 0) {
     contrib0[n] = 0.0;
     contrib1[n] = 0.0;
@@ -206,6 +227,23 @@ __global__ void __launch_bounds__(kBlockThreads) init_kernel(uint64_t n, uint64_
     state->rank_sum = 0.0;
     state->done = 0;
     state->error = 0;
+  }
+}
+
+// iteration 1 only: contrib[0] of the zero-row labels moves from (1/N)/outdeg to ((1-d)/N)/outdeg
+__global__ void __launch_bounds__(kBlockThreads) zero_refresh_kernel(double zero_rank, const uint32_t *outdeg,
+                                                                     double *contrib0, ZeroRanges zr,
+                                                                     IterState *state) {
+  if (ld_volatile_int(&state->done)) return;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t pol = make_evict_first_policy();
+  for (int q = 0; q < kMaxPeers; ++q) {
+    if (q >= zr.world) break;
+    for (uint64_t i = zr.lo[q] + tid; i < zr.hi[q]; i += stride) {
+      const uint32_t od = ld_index(outdeg + i, pol);
+      if (od) st_stream_f64(contrib0 + i, __ddiv_rn(zero_rank, static_cast<double>(od)), pol);
+    }
   }
 }
 
@@ -408,22 +446,6 @@ __global__ void __launch_bounds__(kBlockThreads) heavy_finish_kernel(const Heavy
   block_max_to_state(local_max, a.state);
 }
 
-// ---- zero in-degree rows: rank = (1-d)/N, constant from iteration 1 on -------------------------------
-// Launched for iterations 0 and 1 only, so that BOTH contribution buffers hold base/outdeg.
-__global__ void __launch_bounds__(kBlockThreads) zero_rows_kernel(uint64_t first_row, uint64_t end_row,
-                                                                  IterState *state, const RowEpilogue ep) {
-  if (ld_volatile_int(&state->done)) return;
-  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-  const uint64_t pol = make_evict_first_policy();
-  double local_max = 0.0;
-  for (uint64_t r = first_row + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < end_row;
-       r += stride) {
-    const double d = finish_row(ep, r, 0.0, pol);
-    if (d > local_max) local_max = d;
-  }
-  block_max_to_state(local_max, state);
-}
-
 // ---- cross-partition barrier over the flag pages (P == 1: degenerates to nothing) ---------------------
 
 struct BarrierArgs {
@@ -466,6 +488,7 @@ struct IterEndArgs {
   BarrierArgs bar;
   unsigned long long max_iterations;
   double eps;
+  unsigned long long extra_diff_bits;  // iteration 0: the zero rows' |(1-d)/N - 1/N| (same on every partition)
 };
 
 // End of one iteration: all-reduce(max) of the L-infinity delta across partitions, then the
@@ -475,6 +498,7 @@ __global__ void iter_end_kernel(const IterEndArgs a) {
   if (ld_volatile_int(&st->done)) return;
   const int lane = threadIdx.x & 31;
   unsigned long long bits = st->diff_bits;
+  if (a.extra_diff_bits > bits) bits = a.extra_diff_bits;
   bool ok = true;
   unsigned long long seq = st->barrier_seq;
   if (a.bar.world > 1) {
@@ -658,11 +682,27 @@ BarrierArgs make_barrier(const Graph &g) {
 
 }  // namespace
 
-int launch_init(Graph &g) {
+ZeroRanges make_zero_ranges(const Graph &g) {
+  ZeroRanges zr{};
+  zr.world = static_cast<int>(g.part_world);
+  for (int q = 0; q < kMaxPeers; ++q) {
+    zr.lo[q] = q < zr.world ? g.zero_lo[q] : 0;
+    zr.hi[q] = q < zr.world ? g.zero_hi[q] : 0;
+  }
+  return zr;
+}
+
+// the rank of a zero in-degree row once the loop has run at least once ((1-d)/N); 1/N if it never runs
+double zero_row_rank(const Graph &g, const IterateConfig &cfg) {
+  return cfg.max_iterations == 0 ? 1.0 / static_cast<double>(g.n) : (1.0 - cfg.damping) / static_cast<double>(g.n);
+}
+
+int launch_init(Graph &g, const IterateConfig &cfg) {
   MGB_CUDA(cudaSetDevice(g.device));
   const int grid = grid_for(g, reinterpret_cast<const void *>(init_kernel));
-  init_kernel<<<grid, kBlockThreads, 0, g.stream>>>(g.n, g.local_rows, g.rank, g.outdeg_l, g.contrib(0),
-                                                     g.contrib(1), g.state);
+  init_kernel<<<grid, kBlockThreads, 0, g.stream>>>(g.n, g.local_rows, g.n_heavy + g.n_sell, zero_row_rank(g, cfg),
+                                                     g.rank, g.outdeg_l, g.contrib(0), g.contrib(1),
+                                                     make_zero_ranges(g), g.state);
   MGB_CUDA(cudaGetLastError());
   return MGB200_OK;
 }
@@ -674,7 +714,7 @@ int launch_barrier(Graph &g) {
   return MGB200_OK;
 }
 
-// One iteration.  Main stream: zero rows (iterations 0 and 1 only) -> SELL rows -> heavy segments ->
+// One iteration.  Main stream: (iteration 1: zero-row contribution refresh) -> SELL rows -> heavy segments ->
 // heavy finish -> [join] -> iteration end.  Side stream: the SELL epilogue, forked after the SELL rows:
 // it is the kernel that pushes contributions to the peer GPUs (NVLink-bound), so it overlaps with the
 // heavy-row kernels (L2-gather-bound) instead of queueing behind them.  Every kernel returns immediately
@@ -689,13 +729,10 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     if (!timed) return cudaSuccess;
     return cudaEventRecord(g.kev[(g.timed_launches * Graph::kClasses + cls) * 2 + edge], st);
   };
-  if (g.n_zero > 0 && it < 2) {
-    const uint64_t first = g.n_heavy + g.n_sell;
-    const int grid = static_cast<int>(
-        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(zero_rows_kernel))),
-                 ceil_div(g.n_zero, kBlockThreads)));
+  if (it == 1 && g.any_zero_rows) {
     MGB_CUDA(tick(Graph::kClsZero, 0, g.stream));
-    zero_rows_kernel<<<grid, kBlockThreads, 0, g.stream>>>(first, first + g.n_zero, g.state, ep);
+    zero_refresh_kernel<<<grid_for(g, reinterpret_cast<const void *>(zero_refresh_kernel)), kBlockThreads, 0,
+                          g.stream>>>(zero_row_rank(g, cfg), g.outdeg_l, g.contrib(0), make_zero_ranges(g), g.state);
     MGB_CUDA(tick(Graph::kClsZero, 1, g.stream));
     ++launches;
   }
@@ -790,6 +827,11 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
   e.bar = make_barrier(g);
   e.max_iterations = cfg.max_iterations;
   e.eps = cfg.eps;
+  e.extra_diff_bits = 0ull;
+  if (it == 0 && g.any_zero_rows) {
+    const double zd = fabs(zero_row_rank(g, cfg) - 1.0 / static_cast<double>(g.n));
+    if (zd > 0.0) memcpy(&e.extra_diff_bits, &zd, sizeof(zd));  // NaN / 0 contribute nothing, like the per-row test
+  }
   MGB_CUDA(tick(Graph::kClsIterEnd, 0, g.stream));
   iter_end_kernel<<<1, 32, 0, g.stream>>>(e);
   MGB_CUDA(tick(Graph::kClsIterEnd, 1, g.stream));

@@ -245,6 +245,17 @@ std::vector<double> ComputeRanks(const HostGraph &hg, mgp_graph *graph, int64_t 
   const uint64_t n = hg.gid_of_dense.size();
   std::vector<double> ranks(n);
   if (n == 0) return ranks;
+  // MGB200_GPUS=P (2..8): vertex-partition the call over GPUs 0..P-1 (device-side exchange over NVLink)
+  const char *gpus_env = std::getenv("MGB200_GPUS");
+  const int gpus = gpus_env ? std::atoi(gpus_env) : 1;
+  if (gpus > 1) {
+    uint64_t iterations = 0;
+    const int rc = mgb200_parallel_iterative_pagerank_multi(
+        n, hg.from.size(), hg.from.data(), hg.to.data(), static_cast<uint64_t>(max_iterations), damping_factor,
+        stop_epsilon, threads, static_cast<uint32_t>(gpus), nullptr, ranks.data(), &iterations);
+    if (rc != MGB200_OK) throw ModuleError(mgb200_last_error());
+    return ranks;
+  }
   const char *dev_env = std::getenv("MGB200_DEVICE");
   const int device = dev_env ? std::atoi(dev_env) : 0;
   mgb200_graph *dg = nullptr;

@@ -213,16 +213,16 @@ def parallel_iterative_pagerank(graph, max_iterations=100, damping_factor=0.85, 
 
 
 def pagerank_from_edges(n, sources, targets, max_iterations=100, damping_factor=0.85, stop_epsilon=1e-5,
-                        number_of_threads=1):
-    """One-call form (mgb200_parallel_iterative_pagerank): host COO in, host ranks out."""
+                        number_of_threads=1, gpus=1):
+    """One-call form (mgb200_parallel_iterative_pagerank[_multi]): host COO in, host ranks out."""
     s = np.ascontiguousarray(sources, dtype=np.uint64)
     t = np.ascontiguousarray(targets, dtype=np.uint64)
     out = np.empty(int(n), dtype=np.float64)
     it = ctypes.c_uint64(0)
-    _check(N.lib().mgb200_parallel_iterative_pagerank(int(n), len(s), s.ctypes.data, t.ctypes.data,
-                                                      int(max_iterations) & (2**64 - 1), float(damping_factor),
-                                                      float(stop_epsilon), int(number_of_threads) & 0xFFFFFFFF,
-                                                      out.ctypes.data if n else None, ctypes.byref(it)))
+    _check(N.lib().mgb200_parallel_iterative_pagerank_multi(
+        int(n), len(s), s.ctypes.data, t.ctypes.data, int(max_iterations) & (2**64 - 1), float(damping_factor),
+        float(stop_epsilon), int(number_of_threads) & 0xFFFFFFFF, int(gpus), None, out.ctypes.data if n else None,
+        ctypes.byref(it)))
     return out, it.value
 
 

@@ -78,3 +78,25 @@ def test_partitioned_matches_single_gpu_bitwise_sum():
     multi, results, _ = run_partitioned(mg, n, f, t, 2, max_iterations=20, stop_epsilon=0.0)
     assert float(np.max(np.abs(multi - single) / single)) < 1e-12
     assert abs(multi.sum() - 1.0) < 1e-12
+
+
+def test_one_call_multi_gpu_and_module_env(monkeypatch):
+    """mgb200_parallel_iterative_pagerank_multi (host threads inside the call) and the module's MGB200_GPUS."""
+    if _device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import memgraph_b200 as mg
+    import _fakehost as fh
+    from test_module_host import scattered_graph, oracle_through_module_semantics
+    oracle = Oracle()
+    n, m = 20_000, 150_000
+    rng = np.random.default_rng(3)
+    f, t = rng.integers(0, n, m), rng.integers(0, n, m)
+    got, it = mg.pagerank_from_edges(n, f, t, max_iterations=30, stop_epsilon=0.0, gpus=2)
+    ref, rit = oracle.pagerank(n, f, t, max_iterations=30, stop_epsilon=0.0)
+    assert it == rit and float(np.max(np.abs(got - ref) / ref)) < REL_TOL
+    monkeypatch.setenv("MGB200_GPUS", "2")
+    gids, src, dst = scattered_graph(5000, 40000, seed=9)
+    with fh.Module(fh.MODULE_SO) as module, fh.Graph(gids, src, dst) as g:
+        nodes, ranks = module.call(g, 25, 0.85, 0.0, 1)
+    order, exp, _ = oracle_through_module_semantics(oracle, gids, src, dst, max_iterations=25, stop_epsilon=0.0)
+    assert np.array_equal(nodes, order) and float(np.max(np.abs(ranks - exp) / exp)) < REL_TOL
