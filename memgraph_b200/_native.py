@@ -25,6 +25,11 @@ class RunStatsC(ctypes.Structure):
                 ("kernel_timed_launches", u64), ("class_ms", f64 * 6), ("kernel_launches", u64), ("spmv_launches", u64)]
 
 
+class BfsStats(ctypes.Structure):
+    _fields_ = [("levels", u32), ("top_down_levels", u32), ("bottom_up_levels", u32), ("reached", u64),
+                ("edges_inspected", u64), ("traverse_ms", f64), ("kernel_launches", u64)]
+
+
 ABORT_FN = ctypes.CFUNCTYPE(ctypes.c_int, vp)
 
 
@@ -48,6 +53,11 @@ EXPORTS = {
     "mgb200_graph_export_window": (i32, [vp, vp]),
     "mgb200_graph_connect_peers": (i32, [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]),
     "mgb200_pagerank_run_partition": (i32, [vp, ctypes.POINTER(RunParams), vp, vp, ctypes.POINTER(RunStatsC)]),
+    # include/mgb200_bfs.h
+    "mgb200_bfs_graph_create_device": (i32, [i32, u64, u64, vp, vp, ctypes.POINTER(vp)]),
+    "mgb200_bfs_graph_create_host": (i32, [i32, u64, u64, vp, vp, ctypes.POINTER(vp)]),
+    "mgb200_bfs_graph_destroy": (None, [vp]),
+    "mgb200_bfs_run": (i32, [vp, u64, i32, ctypes.c_int64, ctypes.c_int64, vp, i32, ctypes.POINTER(BfsStats)]),
     "mgb200_rmat_generate_device": (i32, [i32, u32, u64, u64, u64, f64, f64, f64, vp, vp]),
     "mgb200_rmat_generate_host": (i32, [u32, u64, u64, u64, f64, f64, f64, vp, vp]),
     "mgb200_device_malloc": (i32, [i32, ctypes.c_size_t, ctypes.POINTER(vp)]),

@@ -125,3 +125,28 @@ class Reference:
             return self.run(h, n, **kw)
         finally:
             self.free(h)
+
+
+class BfsOracle:
+    """oracle/bfs_oracle.c (same shared object as the PageRank oracle)."""
+    OUT, IN, BOTH = 0, 1, 2
+
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build_checkers()
+        L = ctypes.CDLL(ORACLE_SO)
+        if not hasattr(L, "oracle_bfs"):
+            build_checkers()
+            L = ctypes.CDLL(ORACLE_SO)
+        L.oracle_bfs.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                 ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
+        self.L = L
+
+    def distances(self, n, frm, to, source, direction=0, lower=1, upper=2**63 - 1):
+        frm, to = _u64(frm), _u64(to)
+        out = np.empty(n, dtype=np.int64)
+        rc = self.L.oracle_bfs(n, len(frm), frm.ctypes.data, to.ctypes.data, source, direction, lower, upper,
+                               out.ctypes.data)
+        if rc:
+            raise OracleError(f"oracle_bfs failed: {rc}")
+        return out

@@ -95,11 +95,49 @@ def ref_outputs():
                       "(g++ -std=c++20 -O2, no -funsafe-math-optimizations)", "cases": cases}
 
 
+def bfs_unit_graph():
+    """tests/unit/bfs_common.hpp: the 6-vertex graph kEdges (:46-54) and the expected distances of its own
+    oracle -- Floyd-Warshall over the direction-adjusted edge list (:58-110), then the bounds filter
+    (:452-462: lower -1 -> 0, upper -1 -> vertex count; a == b is never reported)."""
+    text = open(os.path.join(REF, "tests/unit/bfs_common.hpp")).read()
+    block = text[text.index("kEdges = {"):]
+    block = block[:block.index("};")]
+    edges = [[int(a), int(b)] for a, b in re.findall(r"\{(\d+),\s*(\d+),\s*\"[ab]\"\}", block)]
+    n = int(re.search(r"kVertexCount = (\d+)", text).group(1))
+    assert len(edges) == 9 and n == 6
+
+    def floyd_warshall(pairs):
+        inf = 10**9
+        d = [[inf] * n for _ in range(n)]
+        for a, b in pairs:
+            d[a][b] = 1
+        for i in range(n):
+            d[i][i] = 0
+        for k in range(n):
+            for i in range(n):
+                for j in range(n):
+                    if d[i][k] < inf and d[k][j] < inf:
+                        d[i][j] = min(d[i][j], d[i][k] + d[k][j])
+        return [[-1 if x >= inf else x for x in row] for row in d]
+
+    cases = []
+    for name, pairs in [("OUT", edges), ("IN", [[b, a] for a, b in edges]),
+                        ("BOTH", edges + [[b, a] for a, b in edges])]:
+        full = floyd_warshall(pairs)
+        for lower, upper in [(-1, -1), (1, 1), (1, 2), (2, 2), (2, 3), (3, 6), (1, 6)]:
+            lo = 0 if lower == -1 else lower
+            hi = n if upper == -1 else upper
+            dist = [[(full[a][b] if a != b and full[a][b] != -1 and lo <= full[a][b] <= hi else -1) for b in range(n)]
+                    for a in range(n)]
+            cases.append({"direction": name, "lower": lower, "upper": upper, "dist": dist})
+    return {"source": "tests/unit/bfs_common.hpp:42-110,423-470", "n": n, "edges": edges, "cases": cases}
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("reference checkout not present; golden fixtures are committed, nothing to do")
     for name, fn in [("pagerank_unit_vectors.json", unit_vectors), ("pagerank_e2e_cases.json", e2e_cases),
-                     ("pagerank_ref_outputs.json", ref_outputs)]:
+                     ("pagerank_ref_outputs.json", ref_outputs), ("bfs_unit_graph.json", bfs_unit_graph)]:
         with open(os.path.join(HERE, name), "w") as f:
             json.dump(fn(), f, indent=None if "ref_outputs" in name else 1, separators=(",", ":") if "ref_outputs" in name else None)
             f.write("\n")
