@@ -399,6 +399,47 @@ def run_b200_arm(args):
     return 0
 
 
+def run_bfs_arm(args):
+    """Next path (BASELINE config #5): BFS expand on RMAT scale-24, 1 GPU.  value = input edges / traversal
+    time (Graph500-style TEPS) over K seeded sources."""
+    import memgraph_b200 as mg
+    from memgraph_b200 import _native as N
+    from memgraph_b200 import bfs as B
+    lib = N.lib()
+    scale = args.scale if args.scale != 26 else 24
+    n, m = 1 << scale, EDGE_FACTOR << scale
+    d_from = dev_alloc(N, lib, 0, 4 * m)
+    d_to = dev_alloc(N, lib, 0, 4 * m)
+    mg.rmat_edges_device(scale, m, d_from, d_to, seed=SEED, device=0)
+    t0 = time.perf_counter()
+    g = B.BfsGraph.from_device(n, m, d_from, d_to)
+    build_s = time.perf_counter() - t0
+    lib.mgb200_device_free(0, d_from)
+    lib.mgb200_device_free(0, d_to)
+    rng = np.random.default_rng(SEED)
+    sources = [0] + [int(x) for x in rng.integers(0, n, size=max(args.steps + args.warmup, 1))]
+    for s in sources[:max(args.warmup, 3)]:
+        g.distances(s)
+    ms, reached, inspected, launches = [], [], [], 0
+    t0 = time.perf_counter()
+    for s in sources[:args.steps]:
+        dist, st = g.distances(s)
+        ms.append(st["traverse_ms"]); reached.append(st["reached"]); inspected.append(st["edges_inspected"])
+        launches += st["kernel_launches"]
+    e2e_dt = time.perf_counter() - t0
+    total = float(sum(ms))
+    emit({"metric": "bfs_input_edges_per_second", "value": m * args.steps / (total * 1e-3), "unit": "edges/s",
+          "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total / args.steps,
+          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+          "config": {"workload": f"BFS expand (direction OUT, default bounds) RMAT scale-{scale} EF16 (N={n}, E={m}), "
+                                 f"{args.steps} seeded sources", "graph_build_s": build_s,
+                     "reached_per_source": reached, "edges_inspected_per_source": inspected},
+          "e2e": {"value": m * args.steps / e2e_dt, "unit": "edges/s", "h2d_bytes_per_step": 32,
+                  "d2h_bytes_per_step": 4 * n, "api": "mgb200_bfs_run(graph, source, ..., host_dist_out)"},
+          "gpu_launches": launches})
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -409,6 +450,8 @@ def main():
     ap.add_argument("--cpu-scale", type=int, default=int(os.environ.get("MGB200_CPU_SCALE", "22")),
                     help="RMAT scale of the bounded CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="pagerank", choices=["pagerank", "bfs"],
+                    help="pagerank (the BASELINE metric, default) or bfs (the next path, config #5)")
     ap.add_argument("--quick", action="store_true", help="sweep mode: device-resident timing only, compact JSON")
     args = ap.parse_args()
     global REAL_STDOUT
@@ -417,6 +460,8 @@ def main():
     os.dup2(2, 1)  # anything a library prints to stdout lands on stderr; emit() writes the JSON line
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "bfs":
+        return run_bfs_arm(args)
     return run_b200_arm(args)
 
 

@@ -328,7 +328,10 @@ int mgb200_pagerank_run(mgb200_graph *h, const mgb200_run_params *params, double
   if (rc) return rc;
   if (g.n > 0) {
     double *d_out = rank_out;
-    if (!params->rank_out_on_device) MGB_CUDA(cudaMalloc(&d_out, g.n * sizeof(double)));
+    if (!params->rank_out_on_device) {
+      if (!g.out_stage) MGB_CUDA(cudaMalloc(&g.out_stage, g.n * sizeof(double)));  // kept for the handle's life
+      d_out = g.out_stage;
+    }
     rc = launch_write_ranks_original_order(g, d_out);
     if (!rc && !params->rank_out_on_device) {
       cudaError_t e = cudaMemcpyAsync(rank_out, d_out, g.n * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
@@ -336,7 +339,6 @@ int mgb200_pagerank_run(mgb200_graph *h, const mgb200_run_params *params, double
     }
     cudaError_t e = cudaStreamSynchronize(g.stream);
     if (!rc && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
-    if (!params->rank_out_on_device) cudaFree(d_out);
     if (rc) return rc;
   }
   if (stats_out) *stats_out = stats;

@@ -97,6 +97,7 @@ struct Graph {
   IterState *state = nullptr;
   IterState *host_state = nullptr;  // pinned
   double *sum_partials = nullptr;   // [kSumBlocks]
+  double *out_stage = nullptr;      // [n] device staging of the normalised ranks for host-output runs (lazy)
   PeerTable peers{};                // device pointers valid on THIS device
   void *peer_mapped[kMaxPeers] = {};  // IPC mappings to close
   bool peers_connected = false;

@@ -312,6 +312,7 @@ void free_graph(Graph &g) {
     if (g.peer_mapped[q]) cudaIpcCloseMemHandle(g.peer_mapped[q]);
   if (g.sell_item_begin) cudaFree(g.sell_item_begin);
   if (g.sell_sums) cudaFree(g.sell_sums);
+  if (g.out_stage) cudaFree(g.out_stage);
   void *ptrs[] = {g.label_of,  g.outdeg_l,  g.local_vertex, g.heavy_ptr,    g.heavy_idx, g.seg_row,     g.seg_begin,
                   g.seg_first, g.seg_partial, g.sell_colbase, g.sell_idx,     g.rank,      g.window,      g.state,
                   g.sum_partials};

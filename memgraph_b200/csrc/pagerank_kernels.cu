@@ -659,7 +659,7 @@ GatherWindow make_window(const Graph &g) {
   static long l1_hot_k = -1;
   if (l1_hot_k < 0) {
     const char *s = getenv("MGB200_L1_HOT_K");  // in units of 1024 labels; 0 = every gather may allocate in L1
-    l1_hot_k = s ? strtol(s, nullptr, 10) : 24;
+    l1_hot_k = s ? strtol(s, nullptr, 10) : 16;  // sweep: profiles/r01_l1_hot_sweep.txt
     if (l1_hot_k < 0) l1_hot_k = 0;
   }
   w.l1_hot = l1_hot_k == 0 ? 0xFFFFFFFFu : static_cast<uint32_t>(l1_hot_k * 1024);
