@@ -120,7 +120,7 @@ def ncu_traffic():
 
 # ---- reference arm / cpu baseline -------------------------------------------------------------------------
 
-def cpu_reference_run(scale, steps, warmup, threads=None):
+def cpu_reference_run(scale, steps, warmup, threads=None, single_thread_too=False):
     """Times the reference's ParallelIterativePageRank (only that call, like the GPU side) on an RMAT
     graph of `scale`.  Returns dict(value, kind, cores, sample, ms_per_step, build_s)."""
     sys.path.insert(0, os.path.join(REPO, "tests"))
@@ -148,8 +148,14 @@ def cpu_reference_run(scale, steps, warmup, threads=None):
     for _ in range(steps):
         run()
     dt = time.perf_counter() - t0
+    one_thread = None
+    if kind == "reference" and threads > 1 and single_thread_too:
+        t1 = time.perf_counter()
+        impl.run(g, n, max_iterations=ITERATIONS, damping_factor=DAMPING, stop_epsilon=0.0, num_of_threads=1)
+        one_thread = m * ITERATIONS / (time.perf_counter() - t1)
     impl.free(g)
     return {"value": m * ITERATIONS * steps / dt, "unit": "edges/s", "cores": threads, "kind": kind,
+            "value_1_thread": one_thread,
             "sample": f"RMAT scale-{scale} EF{EDGE_FACTOR} (N={n}, E={m}), {ITERATIONS} iterations, stop_epsilon=0, "
                       f"{steps} timed call(s) of ParallelIterativePageRank; graph ctor {build_s:.1f}s excluded",
             "ms_per_step": dt / steps * 1e3, "build_s": build_s}
@@ -373,8 +379,8 @@ def run_b200_arm(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = cpu_reference_run(args.cpu_scale, 1, 0)
-            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            r = cpu_reference_run(args.cpu_scale, 1, 0, single_thread_too=True)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "value_1_thread")}
         except Exception as ex:
             log("cpu_baseline failed:", ex)
 

@@ -59,9 +59,6 @@ __device__ __forceinline__ uint32_t ld_index(const uint32_t *p, uint64_t pol) {
 #endif
 }
 // Gather of one contribution: read-only path; reuse across CTAs lives in L2.
-#ifndef MGB_EXP
-#define MGB_EXP 0  // timing-attribution experiments (WRONG RESULTS): 1 no epilogue, 2 gathers forced into 8 MiB,
-#endif             // 3 no index stream (computed indices), 4 = 2+3, 5 = 1+2+3
 __device__ __forceinline__ double ld_contrib(const double *p, uint64_t pol) {
 #if MGB_GATHER_POLICY
   double v;
@@ -323,8 +320,6 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_
     if (s >= a.n_slices) continue;  // only in the last, partial pass
     const uint32_t width = static_cast<uint32_t>(c1 - c0);
     const uint32_t *p = a.idx + c0 * kSliceRows + lane;
-    const uint64_t cbase = c0;
-    (void)cbase;
     // slice descriptor of this warp's NEXT slice: issued now, consumed after this slice's gathers
     const uint64_t s_next = slice_of(pass + 1);
     if (s_next < a.n_slices) {
@@ -353,17 +348,7 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_
       }
 #else
 #pragma unroll
-      for (int j = 0; j < kUnroll; ++j) {
-#if MGB_EXP == 3 || MGB_EXP == 4 || MGB_EXP == 5
-        src[j] = static_cast<uint32_t>(((cbase + k + j) * 32 + lane) * 2654435761u) % a.window.hot_bytes;
-        src[j] = static_cast<uint32_t>((static_cast<uint64_t>(src[j]) * src[j]) % (a.window.total_bytes / 8));
-#else
-        src[j] = ld_index(p + static_cast<size_t>(k + j) * kSliceRows, pol);
-#endif
-#if MGB_EXP == 2 || MGB_EXP == 4 || MGB_EXP == 5
-        src[j] &= 0xFFFFFu;
-#endif
-      }
+      for (int j = 0; j < kUnroll; ++j) src[j] = ld_index(p + static_cast<size_t>(k + j) * kSliceRows, pol);
 #endif
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib_at(a.contrib_in, src[j], gpol, a.window.l1_hot);

@@ -1,20 +1,18 @@
 // memgraph_b200/csrc/sell_stream.cuh -- the SELL-32 rows as a decoupled, asynchronous stream.
 // (included by pagerank_kernels.cu inside namespace mgb200::{anonymous}, after the shared helpers)
 //
-// Why: the straightforward warp-per-slice loop (sell_rows_kernel) serialises, per 32-row slice,
-// index load -> gather -> tail -> rank/out-degree load -> divide -> store; with ~24 columns per slice on
-// RMAT that is 4-5 dependent memory round trips per 768 edges and the kernel sits at ~38% of every
-// memory unit (profiles/r01_*).  Removing the epilogue alone made it 2.2x faster, i.e. the cost is the
-// drain between slices, not bytes.  Here each warp owns a CONTIGUOUS run of slices = one contiguous
-// span of sell_idx, and three asynchronous stages run ahead of the arithmetic:
+// An alternative to sell_rows_kernel, kept as the documented experiment (opt-in: MGB200_SELL_KERNEL=stream):
+// each warp owns a CONTIGUOUS run of slices = one contiguous span of sell_idx, and two asynchronous stages run
+// ahead of the arithmetic:
 //   1. TMA   : cp.async.bulk streams the span's column indices (4 KiB = 32 columns per chunk) into a
 //              per-warp shared-memory ring, completion on an mbarrier  (SASS: UBLKCP / SYNCS)
 //   2. gather: every lane issues cp.async (LDGSTS) 8-byte copies contrib[idx] -> shared memory for a
 //              batch of 8 columns per commit group, kVals batches deep, no registers held
-//   3. reduce: the lane adds its own landed values in column order (fixed order => deterministic),
-//              and at a slice boundary runs the row epilogue (rank update, contribution for the next
-//              iteration, L-infinity delta)
-// Gathers of later slices are already in flight while an epilogue waits for its rank/out-degree loads.
+//   3. reduce: the lane adds its own landed values in column order (fixed order => deterministic) and
+//              stores the row sum at a slice boundary (the epilogue is sell_epilogue_kernel, as for the rows kernel)
+// Parity-green, but measured slower than the LDG kernel (3.4 vs 2.4 ms at scale-26): the divergent 8-byte LDGSTS
+// costs more per sector in L1TEX than LDG, and deeper rings make it worse (profiles/r01_stream_vs_rows.md).
+// The TMA ring is the right tool for the contiguous index stream; the gather is better left to LDG.
 #pragma once
 
 #ifndef MGB_STREAM_WARPS

@@ -233,3 +233,27 @@ def test_full_size_properties_scale26(mg):
     assert r1.min() >= floor * (1 - 1e-12)
     # vertices with in-degree 0 sit exactly on the floor; RMAT leaves a large fraction there
     assert np.count_nonzero(r1 == r1.min()) == info["zero_rows"]
+
+
+def test_many_small_random_graphs(mg, oracle):
+    """200 seeded random multigraphs (N 1..60, self-loops, parallel edges, isolated vertices, sink-only graphs):
+    ranks and executed-iteration counts equal the oracle's for the default arguments and for a fixed count."""
+    rng = np.random.default_rng(20260921)
+    for trial in range(200):
+        n = int(rng.integers(1, 61))
+        m = int(rng.integers(0, 4 * n + 1))
+        f, t = rng.integers(0, n, m), rng.integers(0, n, m)
+        if trial % 7 == 0 and m:
+            t[:] = t[0]  # a star: one hub destination, many dangling sources
+        kw = dict() if trial % 2 else dict(max_iterations=int(rng.integers(1, 30)), damping_factor=float(rng.uniform(0.05, 0.99)),
+                                           stop_epsilon=0.0)
+        ranks, it = mg.pagerank_from_edges(n, f, t, **kw)
+        ref, rit = oracle.pagerank(n, f, t, **kw)
+        if it != rit:
+            # Only legitimate cause: stop_epsilon == 0 ends the loop when two successive vectors are BIT-identical,
+            # which depends on the order of additions inside a row (the reference's own count changes with its
+            # thread count).  Tiny graphs reach an exact fixed point; then both runs stopped early, on the same
+            # fixed point.  With a positive epsilon, or when the iteration cap is hit, the counts must agree.
+            assert kw.get("stop_epsilon", 1e-5) == 0.0 and it < kw["max_iterations"] and rit < kw["max_iterations"], \
+                (trial, n, m, kw, it, rit)
+        assert rel_err(ranks, ref) < REL_TOL, (trial, n, m, kw)
