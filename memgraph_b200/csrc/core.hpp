@@ -62,6 +62,7 @@ struct Graph {
   uint64_t local_edges = 0;
   uint64_t n_heavy = 0, n_sell = 0, n_zero = 0;
   uint32_t heavy_min_degree = 0, segment_edges = 0;
+  uint64_t part_start[kMaxPeers] = {};  // first global label of every partition
   uint64_t zero_lo[kMaxPeers] = {}, zero_hi[kMaxPeers] = {};  // global label range of every partition's zero rows
   bool any_zero_rows = false;
 

@@ -450,6 +450,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     MGB_CUDA(cudaStreamSynchronize(st));
     g.any_zero_rows = false;
     for (uint32_t q = 0; q < g.part_world; ++q) {
+      g.part_start[q] = deal.start(q);
       g.zero_lo[q] = deal.start(q) + nz_host[q];
       g.zero_hi[q] = deal.start(q) + deal.count(q);
       if (g.zero_hi[q] > g.zero_lo[q]) g.any_zero_rows = true;

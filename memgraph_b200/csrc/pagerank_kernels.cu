@@ -69,36 +69,62 @@ __device__ __forceinline__ double ld_contrib(const double *p, uint64_t pol) {
   return __ldg(p);
 #endif
 }
-// L2 residency plan (measured, scripts/l2_bench.cu): random gathers run at ~275 G/s while the gathered
-// set fits ~64 MiB of L2 and at ~49 G/s from HBM.  Labels are sorted by degree, so the hot vertices are
-// the PREFIX of contrib[]: that prefix is loaded evict_last, everything else that streams through L2
-// (cold tail of contrib[], index arrays, rank / out-degree / contrib_out traffic) is evict_first.
+// L2 / L1 residency plan (measured, scripts/l2_bench.cu, scripts/gather_bench.cu): random gathers run at
+// ~275 G/s while the gathered set fits ~64 MiB of L2 and at ~49 G/s from HBM; an SM issues one L2 request per
+// cycle, so every L1 hit is a request saved, and with plain LRU the 86 % of gathers that miss evict the hottest
+// lines (14 % L1 hit rate).  Labels are sorted by degree, so "hot" is a property of the label alone:
+//   one partition : the hot vertices are the PREFIX of contrib[]            -> local index = label
+//   P partitions  : sorted positions are dealt round-robin, every partition's label range starts with ITS
+//                   hottest vertices                                          -> local index = label - start[owner]
+// local < l2_hot: L2 evict_last, else evict_first (like every other stream: indices, rank, out-degree, contrib_out);
+// local < l1_hot: may allocate in L1 (evict_last), else bypasses it.
 struct GatherWindow {
-  uint32_t hot_bytes;    // primary (evict_last) span, from contrib_in
+  uint32_t hot_bytes;    // single partition: primary (evict_last) span of the range policy, from contrib_in
   uint32_t total_bytes;  // whole vector (secondary span: evict_first)
-  uint32_t l1_hot;       // labels below this may allocate in L1; colder gathers bypass it (no pollution)
+  uint32_t l1_hot;       // local indices below this may allocate in L1
+  uint32_t l2_hot;       // local indices below this are L2 evict_last (multi-partition form)
+  uint32_t world;        // number of partitions
+  uint32_t start[kMaxPeers];  // first global label of every partition
 };
-// The SM issues one L2 request per cycle (148 x 1.965 GHz = 290 G/s, which is where both gather kernels sit),
-// so every L1 hit is a request saved.  L1 holds ~28 K doubles; with plain LRU the 86 % of gathers that miss
-// keep evicting the hottest lines (14 % hit rate measured).  Only the hottest labels may allocate.
-__device__ __forceinline__ double ld_contrib_at(const double *base, uint32_t src, uint64_t pol, uint32_t l1_hot) {
-  double v;
-  if (src < l1_hot)
-    asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(base + src), "l"(pol));
-  else
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(base + src), "l"(pol));
-  return v;
+constexpr uint32_t kL1Plain = 0xFFFFFFFFu;  // GatherWindow::l1_hot value meaning "no L1 hints"
+struct GatherPolicy {
+  uint64_t hot;   // single partition: the range policy; else fractional evict_last
+  uint64_t cold;  // fractional evict_first
+};
+__device__ __forceinline__ GatherPolicy make_gather_policy(const double *contrib_in, const GatherWindow &w) {
+  GatherPolicy p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.cold));
+  if (w.world <= 1 || w.l2_hot == 0xFFFFFFFFu) {  // single partition, or partition-unaware legacy mode
+    asm volatile("createpolicy.range.global.L2::evict_last.L2::evict_first.b64 %0, [%1], %2, %3;"
+                 : "=l"(p.hot)
+                 : "l"(contrib_in), "r"(w.hot_bytes), "r"(w.total_bytes));
+  } else {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.hot));
+  }
+  return p;
 }
-__device__ __forceinline__ uint64_t make_gather_policy(const double *contrib_in, GatherWindow w) {
-  uint64_t pol;
-#if MGB_GATHER_POLICY == 2
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-#else
-  asm volatile("createpolicy.range.global.L2::evict_last.L2::evict_first.b64 %0, [%1], %2, %3;"
-               : "=l"(pol)
-               : "l"(contrib_in), "r"(w.hot_bytes), "r"(w.total_bytes));
-#endif
-  return pol;
+template <bool kMulti>
+__device__ __forceinline__ double ld_contrib_at(const double *base, uint32_t src, const GatherPolicy &gp,
+                                                const GatherWindow &w) {
+  uint32_t local = src;
+  uint64_t pol = gp.hot;
+  if (kMulti) {
+    uint32_t s0 = 0;
+#pragma unroll
+    for (int q = 1; q < kMaxPeers; ++q)
+      if (q < static_cast<int>(w.world) && src >= w.start[q]) s0 = w.start[q];
+    local = src - s0;
+    pol = local < w.l2_hot ? gp.hot : gp.cold;
+  }
+  double v;
+  if (w.l1_hot == kL1Plain) {  // default L1 policy for every gather
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(base + src), "l"(pol));
+  } else if (local < w.l1_hot) {
+    asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(base + src), "l"(pol));
+  } else {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(base + src), "l"(pol));
+  }
+  return v;
 }
 __device__ __forceinline__ double ld_stream_f64(const double *p, uint64_t pol) {
 #if MGB_EPI_HINT
@@ -297,11 +323,12 @@ __global__ void __launch_bounds__(kBlockThreads) sell_epilogue_kernel(uint64_t f
 #define MGB_SELL_PREFETCH 0    // 1: load the next batch of column indices before consuming the current gathers
 #endif
 
+template <bool kMulti>
 __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_kernel(const SellArgs a) {
   if (ld_volatile_int(&a.state->done)) return;
   const int lane = threadIdx.x & 31;
   const uint64_t pol = make_evict_first_policy();
-  const uint64_t gpol = make_gather_policy(a.contrib_in, a.window);
+  const GatherPolicy gpol = make_gather_policy(a.contrib_in, a.window);
   const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * kWarpsPerBlock;
   const uint64_t warp0 = static_cast<uint64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   // Slices are sorted by width (descending), so a plain warp-strided walk gives warp 0 up to one full
@@ -351,7 +378,7 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_
       for (int j = 0; j < kUnroll; ++j) src[j] = ld_index(p + static_cast<size_t>(k + j) * kSliceRows, pol);
 #endif
 #pragma unroll
-      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib_at(a.contrib_in, src[j], gpol, a.window.l1_hot);
+      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib_at<kMulti>(a.contrib_in, src[j], gpol, a.window);
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) acc += v[j];  // fixed order: ascending source label
     }
@@ -363,7 +390,7 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_
         if (k + j < width) src[j] = ld_index(p + static_cast<size_t>(k + j) * kSliceRows, pol);
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j)
-        if (k + j < width) v[j] = ld_contrib_at(a.contrib_in, src[j], gpol, a.window.l1_hot);
+        if (k + j < width) v[j] = ld_contrib_at<kMulti>(a.contrib_in, src[j], gpol, a.window);
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j)
         if (k + j < width) acc += v[j];
@@ -393,13 +420,14 @@ struct HeavyArgs {
   RowEpilogue ep;
 };
 
-__global__ void __launch_bounds__(kBlockThreads) heavy_segments_kernel(const HeavyArgs a) {
+template <bool kMulti>
+__global__ void __launch_bounds__(kBlockThreads, 8) heavy_segments_kernel(const HeavyArgs a) {
   if (ld_volatile_int(&a.state->done)) return;
   const int lane = threadIdx.x & 31;
   const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * kWarpsPerBlock;
   const uint64_t warp0 = static_cast<uint64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   const uint64_t pol = make_evict_first_policy();
-  const uint64_t gpol = make_gather_policy(a.contrib_in, a.window);
+  const GatherPolicy gpol = make_gather_policy(a.contrib_in, a.window);
   for (uint64_t g = warp0; g < a.n_seg; g += warps_total) {
     const uint32_t r = a.seg_row[g];
     const uint64_t e0 = a.seg_begin[g];
@@ -413,11 +441,11 @@ __global__ void __launch_bounds__(kBlockThreads) heavy_segments_kernel(const Hea
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) src[j] = ld_index(a.heavy_idx + e + 32ull * j, pol);
 #pragma unroll
-      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib_at(a.contrib_in, src[j], gpol, a.window.l1_hot);
+      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib_at<kMulti>(a.contrib_in, src[j], gpol, a.window);
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) acc += v[j];
     }
-    for (; e < e1; e += 32) acc += ld_contrib_at(a.contrib_in, ld_index(a.heavy_idx + e, pol), gpol, a.window.l1_hot);
+    for (; e < e1; e += 32) acc += ld_contrib_at<kMulti>(a.contrib_in, ld_index(a.heavy_idx + e, pol), gpol, a.window);
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(kFull, acc, o);  // fixed tree
     if (lane == 0) a.seg_partial[g] = acc;
   }
@@ -644,10 +672,21 @@ GatherWindow make_window(const Graph &g) {
   static long l1_hot_k = -1;
   if (l1_hot_k < 0) {
     const char *s = getenv("MGB200_L1_HOT_K");  // in units of 1024 labels; 0 = every gather may allocate in L1
-    l1_hot_k = s ? strtol(s, nullptr, 10) : 16;  // sweep: profiles/r01_l1_hot_sweep.txt
-    if (l1_hot_k < 0) l1_hot_k = 0;
+    l1_hot_k = s ? strtol(s, nullptr, 10) : 16;  // sweep: profiles/r01_l1_hot_sweep.txt; negative = no L1 hints
   }
-  w.l1_hot = l1_hot_k == 0 ? 0xFFFFFFFFu : static_cast<uint32_t>(l1_hot_k * 1024);
+  static int multi_aware = -1;
+  if (multi_aware < 0) {
+    const char *s = getenv("MGB200_MULTI_AWARE");  // 0: treat the global label prefix as hot on every partition (legacy)
+    multi_aware = (s && s[0] == '0') ? 0 : 1;
+  }
+  w.world = g.part_world;
+  const uint32_t div = multi_aware ? g.part_world : 1;
+  w.l1_hot = l1_hot_k < 0 ? kL1Plain
+                          : static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(l1_hot_k) * 1024 / div, 0xFFFFFFF0ull));
+  w.l2_hot = multi_aware ? static_cast<uint32_t>((static_cast<uint64_t>(hot_mb) << 20) / sizeof(double) / g.part_world)
+                         : 0xFFFFFFFFu;
+  for (uint32_t q = 0; q < static_cast<uint32_t>(kMaxPeers); ++q)
+    w.start[q] = q < g.part_world ? static_cast<uint32_t>(g.part_start[q]) : 0xFFFFFFFFu;
   return w;
 }
 
@@ -774,10 +813,15 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
       const int sgrid = static_cast<int>(std::min<uint64_t>(g.sm_count, ceil_div(g.sell_items, kStreamWarps)));
       sell_stream_kernel<<<sgrid, kStreamThreads, kStreamSmemBytes, g.stream>>>(t);
     } else {
+      const bool multi = s.window.world > 1 && s.window.l2_hot != 0xFFFFFFFFu;
+      const void *fn = multi ? reinterpret_cast<const void *>(sell_rows_kernel<true>)
+                             : reinterpret_cast<const void *>(sell_rows_kernel<false>);
       const int grid = static_cast<int>(
-          std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_rows_kernel))),
-                   ceil_div(g.n_slices, kWarpsPerBlock)));
-      sell_rows_kernel<<<grid, kBlockThreads, 0, g.stream>>>(s);
+          std::min(static_cast<uint64_t>(grid_for(g, fn)), ceil_div(g.n_slices, kWarpsPerBlock)));
+      if (multi)
+        sell_rows_kernel<true><<<grid, kBlockThreads, 0, g.stream>>>(s);
+      else
+        sell_rows_kernel<false><<<grid, kBlockThreads, 0, g.stream>>>(s);
     }
     MGB_CUDA(tick(Graph::kClsSell, 1, g.stream));
     // fork: epilogue on the side stream
@@ -812,11 +856,15 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     h.window = make_window(g);
     h.state = g.state;
     h.ep = ep;
-    int grid = static_cast<int>(
-        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_segments_kernel))),
-                 ceil_div(g.n_seg, kWarpsPerBlock)));
+    const bool multi = h.window.world > 1 && h.window.l2_hot != 0xFFFFFFFFu;
+    const void *hfn = multi ? reinterpret_cast<const void *>(heavy_segments_kernel<true>)
+                            : reinterpret_cast<const void *>(heavy_segments_kernel<false>);
+    int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_for(g, hfn)), ceil_div(g.n_seg, kWarpsPerBlock)));
     MGB_CUDA(tick(Graph::kClsHeavySeg, 0, g.stream));
-    heavy_segments_kernel<<<grid, kBlockThreads, 0, g.stream>>>(h);
+    if (multi)
+      heavy_segments_kernel<true><<<grid, kBlockThreads, 0, g.stream>>>(h);
+    else
+      heavy_segments_kernel<false><<<grid, kBlockThreads, 0, g.stream>>>(h);
     MGB_CUDA(tick(Graph::kClsHeavySeg, 1, g.stream));
     grid = static_cast<int>(
         std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_finish_kernel))),
@@ -877,8 +925,8 @@ int launch_write_ranks_local(Graph &g, double *d_rank_out, uint32_t *d_vertex_ou
 
 int kernel_occupancy_report(Graph &g, char *buf, size_t cap) {
   int a = 0, b = 0, c = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sell_rows_kernel, kBlockThreads, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, heavy_segments_kernel, kBlockThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sell_rows_kernel<false>, kBlockThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, heavy_segments_kernel<false>, kBlockThreads, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, heavy_finish_kernel, kBlockThreads, 0);
   snprintf(buf, cap, "sm=%d blocks/SM: sell=%d heavy_seg=%d heavy_fin=%d (block=%d threads)", g.sm_count, a, b, c,
            kBlockThreads);

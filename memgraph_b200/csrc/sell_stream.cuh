@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) sell_stream_kernel(const Se
   }
   __syncwarp();
   const uint64_t pol = make_evict_first_policy();
-  const uint64_t gpol = make_gather_policy(a.contrib_in, a.window);
+  const uint64_t gpol = make_gather_policy(a.contrib_in, a.window).hot;
   const uint32_t warps_total = gridDim.x * kStreamWarps;
   uint32_t chunks_done = 0;  // chunks consumed so far by this warp over all items (drives slot/parity)
 

@@ -252,8 +252,9 @@ def test_many_small_random_graphs(mg, oracle):
         if it != rit:
             # Only legitimate cause: stop_epsilon == 0 ends the loop when two successive vectors are BIT-identical,
             # which depends on the order of additions inside a row (the reference's own count changes with its
-            # thread count).  Tiny graphs reach an exact fixed point; then both runs stopped early, on the same
-            # fixed point.  With a positive epsilon, or when the iteration cap is hit, the counts must agree.
-            assert kw.get("stop_epsilon", 1e-5) == 0.0 and it < kw["max_iterations"] and rit < kw["max_iterations"], \
+            # thread count).  Tiny graphs sit on an exact fixed point up to rounding noise: one side sees two
+            # identical vectors an iteration or two before the other (which may dither in the last bit until the
+            # cap).  The ranks still agree to rounding (asserted below).  With a positive epsilon the counts must agree.
+            assert kw.get("stop_epsilon", 1e-5) == 0.0 and min(it, rit) < kw["max_iterations"], \
                 (trial, n, m, kw, it, rit)
         assert rel_err(ranks, ref) < REL_TOL, (trial, n, m, kw)
