@@ -17,6 +17,7 @@
 
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "mgb200_pagerank.h"
 
@@ -89,6 +90,7 @@ struct Graph {
   double *sell_sums = nullptr;       // [n_sell] per-row gathered sums of the current iteration
   uint32_t sell_items = 0;           // work items of the streaming kernel: contiguous slice runs, ~equal columns
   uint64_t *sell_item_begin = nullptr;  // [sell_items + 1] first slice of each item
+  std::vector<uint64_t> sell_item_begin_host;  // host copy (chunked launches of the SELL class)
 
   // iteration state
   double *rank = nullptr;      // [local_rows] un-normalised ranks, updated in place
@@ -108,7 +110,9 @@ struct Graph {
   cudaEvent_t ev[4] = {};
   // side stream for the SELL epilogue (overlaps the peer push with the heavy-row kernels)
   cudaStream_t stream2 = nullptr;
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  static constexpr int kMaxChunks = 8;
+  cudaEvent_t fork_evs[kMaxChunks] = {};
+  cudaEvent_t join_ev = nullptr;
   bool overlap_epilogue = true;
   // optional per-launch timing: an event pair around every kernel of the first kMaxTimedLaunches iterations
   static constexpr int kMaxTimedLaunches = 64;

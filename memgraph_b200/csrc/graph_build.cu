@@ -323,7 +323,8 @@ void free_graph(Graph &g) {
     if (e) cudaEventDestroy(e);
   for (auto &e : g.kev)
     if (e) cudaEventDestroy(e);
-  if (g.fork_ev) cudaEventDestroy(g.fork_ev);
+  for (auto &e : g.fork_evs)
+    if (e) cudaEventDestroy(e);
   if (g.join_ev) cudaEventDestroy(g.join_ev);
   if (g.stream2) cudaStreamDestroy(g.stream2);
   if (g.stream) cudaStreamDestroy(g.stream);
@@ -336,7 +337,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   g.sm_count = prop.multiProcessorCount;
   MGB_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   MGB_CUDA(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
-  MGB_CUDA(cudaEventCreateWithFlags(&g.fork_ev, cudaEventDisableTiming));
+  for (auto &e : g.fork_evs) MGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   MGB_CUDA(cudaEventCreateWithFlags(&g.join_ev, cudaEventDisableTiming));
   {
     const char *s = getenv("MGB200_OVERLAP_EPILOGUE");
@@ -569,6 +570,10 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     MGB_CUDA(keep_alloc(g, &g.sell_item_begin, static_cast<uint64_t>(g.sell_items) + 1));
     sell_items_kernel<<<(g.sell_items + 1 + kThreads - 1) / kThreads, kThreads, 0, st>>>(
         g.sell_items, g.n_slices, g.sell_colbase, total_cols, g.sell_item_begin);
+    g.sell_item_begin_host.resize(static_cast<size_t>(g.sell_items) + 1);
+    MGB_CUDA(cudaMemcpyAsync(g.sell_item_begin_host.data(), g.sell_item_begin,
+                             g.sell_item_begin_host.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    MGB_CUDA(cudaStreamSynchronize(st));
   }
   MGB_CUDA(cudaGetLastError());
   MGB_CUDA(cudaEventRecord(g.ev[1], st));

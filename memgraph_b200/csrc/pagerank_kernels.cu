@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(kBlockThreads) zero_refresh_kernel(double zero
 struct SellArgs {
   const uint64_t *colbase;
   const uint32_t *idx;
+  uint64_t slice_begin;  // this launch covers slices [slice_begin, slice_begin + n_slices)
   uint64_t n_slices;
   uint64_t first_row;  // local row of slice 0, lane 0
   uint64_t end_row;    // first local row past the SELL class
@@ -339,8 +340,8 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_
   };
   uint64_t c0 = 0, c1 = 0;
   if (slice_of(0) < a.n_slices) {
-    c0 = a.colbase[slice_of(0)];
-    c1 = a.colbase[slice_of(0) + 1];
+    c0 = a.colbase[a.slice_begin + slice_of(0)];
+    c1 = a.colbase[a.slice_begin + slice_of(0) + 1];
   }
   for (uint64_t pass = 0; pass * warps_total < a.n_slices; ++pass) {
     const uint64_t s = slice_of(pass);
@@ -350,8 +351,8 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_
     // slice descriptor of this warp's NEXT slice: issued now, consumed after this slice's gathers
     const uint64_t s_next = slice_of(pass + 1);
     if (s_next < a.n_slices) {
-      c0 = a.colbase[s_next];
-      c1 = a.colbase[s_next + 1];
+      c0 = a.colbase[a.slice_begin + s_next];
+      c1 = a.colbase[a.slice_begin + s_next + 1];
     }
     double acc = 0.0;
     uint32_t k = 0;
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_
       for (int j = 0; j < kUnroll; ++j)
         if (k + j < width) acc += v[j];
     }
-    const uint64_t row = a.first_row + s * kSliceRows + lane;
+    const uint64_t row = a.first_row + (a.slice_begin + s) * kSliceRows + lane;
     if (row < a.end_row) a.sums[row - a.first_row] = acc;  // epilogue runs as its own elementwise kernel
   }
 }
@@ -784,6 +785,7 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     SellArgs s{};
     s.colbase = g.sell_colbase;
     s.idx = g.sell_idx;
+    s.slice_begin = 0;
     s.n_slices = g.n_slices;
     s.first_row = g.n_heavy;
     s.end_row = g.n_heavy + g.n_sell;
@@ -791,8 +793,24 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     s.window = make_window(g);
     s.state = g.state;
     s.sums = g.sell_sums;
+    // The SELL class can run as `chunks` launches over contiguous slice ranges of ~equal column counts, with the
+    // epilogue (+ NVLink push) of chunk c forked to the side stream as soon as chunk c's sums exist
+    // (MGB200_SELL_CHUNKS).  Default 1: at 2/4/8 GPUs the extra launches cost more than the earlier push saves.
+    const bool stream_kernel = use_stream_kernel() && g.sell_items > 0;
+    int chunks = 1;
+    if (!stream_kernel && g.overlap_epilogue && !g.sell_item_begin_host.empty()) {
+      static int env_chunks = -1;
+      if (env_chunks < 0) {
+        const char *e = getenv("MGB200_SELL_CHUNKS");
+        env_chunks = e ? atoi(e) : 0;
+      }
+      chunks = env_chunks > 0 ? env_chunks : 1;  // measured: no gain from chunking at 2/4/8 GPUs (profiles/r01_multi_gpu.md)
+      chunks = std::max(1, std::min(chunks, Graph::kMaxChunks));
+    }
+    cudaStream_t es = g.overlap_epilogue ? g.stream2 : g.stream;
+    const int egrid_full = grid_for(g, reinterpret_cast<const void *>(sell_epilogue_kernel));
     MGB_CUDA(tick(Graph::kClsSell, 0, g.stream));
-    if (use_stream_kernel() && g.sell_items > 0) {
+    if (stream_kernel) {
       static bool attr_set = false;
       if (!attr_set) {
         MGB_CUDA(cudaFuncSetAttribute(sell_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -812,33 +830,45 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
       t.sums = g.sell_sums;
       const int sgrid = static_cast<int>(std::min<uint64_t>(g.sm_count, ceil_div(g.sell_items, kStreamWarps)));
       sell_stream_kernel<<<sgrid, kStreamThreads, kStreamSmemBytes, g.stream>>>(t);
-    } else {
-      const bool multi = s.window.world > 1 && s.window.l2_hot != 0xFFFFFFFFu;
-      const void *fn = multi ? reinterpret_cast<const void *>(sell_rows_kernel<true>)
-                             : reinterpret_cast<const void *>(sell_rows_kernel<false>);
-      const int grid = static_cast<int>(
-          std::min(static_cast<uint64_t>(grid_for(g, fn)), ceil_div(g.n_slices, kWarpsPerBlock)));
-      if (multi)
-        sell_rows_kernel<true><<<grid, kBlockThreads, 0, g.stream>>>(s);
-      else
-        sell_rows_kernel<false><<<grid, kBlockThreads, 0, g.stream>>>(s);
     }
-    MGB_CUDA(tick(Graph::kClsSell, 1, g.stream));
-    // fork: epilogue on the side stream
-    cudaStream_t es = g.overlap_epilogue ? g.stream2 : g.stream;
-    if (g.overlap_epilogue) {
-      MGB_CUDA(cudaEventRecord(g.fork_ev, g.stream));
-      MGB_CUDA(cudaStreamWaitEvent(g.stream2, g.fork_ev, 0));
-      forked = true;
+    const bool multi = s.window.world > 1 && s.window.l2_hot != 0xFFFFFFFFu;
+    const void *fn = multi ? reinterpret_cast<const void *>(sell_rows_kernel<true>)
+                           : reinterpret_cast<const void *>(sell_rows_kernel<false>);
+    const int grid_full = grid_for(g, fn);
+    for (int c = 0; c < chunks; ++c) {
+      uint64_t sb = 0, se = g.n_slices;
+      if (chunks > 1) {
+        sb = g.sell_item_begin_host[static_cast<size_t>(c) * g.sell_items / chunks];
+        se = g.sell_item_begin_host[static_cast<size_t>(c + 1) * g.sell_items / chunks];
+      }
+      if (!stream_kernel && se > sb) {
+        s.slice_begin = sb;
+        s.n_slices = se - sb;
+        const int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_full), ceil_div(se - sb, kWarpsPerBlock)));
+        if (multi)
+          sell_rows_kernel<true><<<grid, kBlockThreads, 0, g.stream>>>(s);
+        else
+          sell_rows_kernel<false><<<grid, kBlockThreads, 0, g.stream>>>(s);
+        ++launches;
+      }
+      if (c == chunks - 1) MGB_CUDA(tick(Graph::kClsSell, 1, g.stream));
+      if (g.overlap_epilogue) {
+        MGB_CUDA(cudaEventRecord(g.fork_evs[c], g.stream));
+        MGB_CUDA(cudaStreamWaitEvent(g.stream2, g.fork_evs[c], 0));
+        forked = true;
+      }
+      const uint64_t r0 = s.first_row + sb * kSliceRows;
+      const uint64_t r1 = std::min<uint64_t>(s.end_row, s.first_row + se * kSliceRows);
+      if (r1 > r0) {
+        const int egrid = static_cast<int>(std::min(static_cast<uint64_t>(egrid_full), ceil_div(r1 - r0, kBlockThreads)));
+        if (c == 0) MGB_CUDA(tick(Graph::kClsSellEpi, 0, es));
+        sell_epilogue_kernel<<<egrid, kBlockThreads, 0, es>>>(r0, r1, g.sell_sums + (r0 - s.first_row), g.state, ep);
+        ++launches;
+      }
+      if (c == chunks - 1) MGB_CUDA(tick(Graph::kClsSellEpi, 1, es));
     }
-    const int egrid = static_cast<int>(
-        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_epilogue_kernel))),
-                 ceil_div(g.n_sell, kBlockThreads)));
-    MGB_CUDA(tick(Graph::kClsSellEpi, 0, es));
-    sell_epilogue_kernel<<<egrid, kBlockThreads, 0, es>>>(s.first_row, s.end_row, g.sell_sums, g.state, ep);
-    MGB_CUDA(tick(Graph::kClsSellEpi, 1, es));
+    if (stream_kernel) ++launches;
     if (forked) MGB_CUDA(cudaEventRecord(g.join_ev, g.stream2));
-    launches += 2;
     if (spmv_count) *spmv_count += 1;
   }
   if (g.n_seg > 0) {
