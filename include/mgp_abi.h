@@ -87,6 +87,7 @@ enum mgp_error mgp_value_make_vertex(struct mgp_vertex *val, struct mgp_value **
 enum mgp_error mgp_value_get_int(struct mgp_value *val, int64_t *result);                               /* :436 */
 enum mgp_error mgp_value_get_double(struct mgp_value *val, double *result);                             /* :441 */
 enum mgp_error mgp_list_at(struct mgp_list *list, size_t index, struct mgp_value **result); /* :563 borrowed */
+enum mgp_error mgp_value_get_vertex(struct mgp_value *val, struct mgp_vertex **result);     /* :461 borrowed; gpu_bfs only */
 
 /* ---- result rows ---- */
 enum mgp_error mgp_result_set_error_msg(struct mgp_result *res, const char *error_msg);                 /* :716 */
@@ -119,6 +120,7 @@ enum mgp_error mgp_type_float(struct mgp_type **result);                        
 enum mgp_error mgp_type_node(struct mgp_type **result);                                                 /* :1725 */
 enum mgp_error mgp_module_add_read_procedure(struct mgp_module *module, const char *name, mgp_proc_cb cb,
                                              struct mgp_proc **result);                                 /* :1838 */
+enum mgp_error mgp_proc_add_arg(struct mgp_proc *proc, const char *name, struct mgp_type *type); /* :1890 gpu_bfs only */
 enum mgp_error mgp_proc_add_opt_arg(struct mgp_proc *proc, const char *name, struct mgp_type *type,
                                     struct mgp_value *default_value); /* :1914 default is copied */
 enum mgp_error mgp_proc_add_result(struct mgp_proc *proc, const char *name, struct mgp_type *type);     /* :1928 */

@@ -31,11 +31,12 @@ NVCC_FLAGS = [
 CUDA_SOURCES = ["pagerank_kernels.cu", "graph_build.cu", "capi.cu", "bfs.cu"]
 HEADERS = [os.path.join(CSRC, "core.hpp"), os.path.join(CSRC, "rmat.hpp"), os.path.join(CSRC, "sell_stream.cuh"),
            os.path.join(INCLUDE, "mgb200_pagerank.h"), os.path.join(INCLUDE, "mgb200_bfs.h"),
-           os.path.join(INCLUDE, "mgp_abi.h")]
+           os.path.join(INCLUDE, "mgp_abi.h"), os.path.join(CSRC, "mgp_module_common.hpp")]
 
 CORE_LIB = os.path.join(OUT, "libmgb200_pagerank.so")
 MODULE_LIB = os.path.join(OUT, "pagerank.so")
 FAKE_HOST_LIB = os.path.join(OUT, "libmgp_fake_host.so")
+BFS_MODULE_LIB = os.path.join(OUT, "gpu_bfs.so")
 
 
 def _newer(target, deps):
@@ -86,6 +87,18 @@ def build_module(objs, verbose=False):
         _run([NVCC, "-shared", "-cudart", "static", "-o", MODULE_LIB, obj] + objs)
 
 
+def build_bfs_module(objs, verbose=False):
+    """gpu_bfs.so: the breadth-first expansion as a read procedure (same linking rules as pagerank.so)."""
+    src = os.path.join(CSRC, "gpu_bfs_module.cpp")
+    obj = os.path.join(OUT, "gpu_bfs_module.o")
+    if _newer(obj, [src] + HEADERS):
+        if verbose:
+            print("g++ gpu_bfs_module.cpp", flush=True)
+        _run([CXX, "-std=c++20", "-O2", "-fPIC", "-fvisibility=hidden", "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj])
+    if _newer(BFS_MODULE_LIB, objs + [obj]):
+        _run([NVCC, "-shared", "-cudart", "static", "-o", BFS_MODULE_LIB, obj] + objs)
+
+
 def build_fake_host(verbose=False):
     src = os.path.join(CSRC, "mgp_fake_host.cpp")
     if _newer(FAKE_HOST_LIB, [src] + HEADERS):
@@ -100,7 +113,11 @@ def build_all(verbose=False):
         build_module(objs, verbose)
     if os.path.exists(os.path.join(CSRC, "mgp_fake_host.cpp")):
         build_fake_host(verbose)
+    if os.path.exists(os.path.join(CSRC, "gpu_bfs_module.cpp")):
+        build_bfs_module(objs, verbose)
     out = {"core": CORE_LIB}
+    if os.path.exists(os.path.join(CSRC, "gpu_bfs_module.cpp")):
+        out["bfs_module"] = BFS_MODULE_LIB
     if os.path.exists(os.path.join(CSRC, "pagerank_module.cpp")):
         out["module"] = MODULE_LIB
     if os.path.exists(os.path.join(CSRC, "mgp_fake_host.cpp")):

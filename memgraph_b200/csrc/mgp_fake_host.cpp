@@ -105,6 +105,7 @@ struct ProcArg {
   std::string name;
   mgp_type *type;
   mgp_value default_value;
+  bool required = false;
 };
 
 struct mgp_proc {
@@ -366,6 +367,21 @@ mgp_error mgp_module_add_read_procedure(mgp_module *module, const char *name, mg
   *result = &p;
   return OK;
 }
+mgp_error mgp_proc_add_arg(mgp_proc *proc, const char *name, mgp_type *type) {  // :4880-4920
+  if (!ValidIdentifier(name)) return mgp_error::MGP_ERROR_INVALID_ARGUMENT;
+  for (auto &a : proc->opt_args)
+    if (!a.required) return mgp_error::MGP_ERROR_LOGIC_ERROR;  // required args must precede optional ones
+  ProcArg a;
+  a.name = name;
+  a.type = type;
+  a.required = true;
+  proc->opt_args.push_back(a);
+  return OK;
+}
+mgp_error mgp_value_get_vertex(mgp_value *val, mgp_vertex **result) {  // unchecked union read in the real host
+  *result = val->vertex;
+  return OK;
+}
 mgp_error mgp_proc_add_opt_arg(mgp_proc *proc, const char *name, mgp_type *type, mgp_value *default_value) {
   if (!ValidIdentifier(name)) return mgp_error::MGP_ERROR_INVALID_ARGUMENT;
   if (default_value->kind == ValueKind::Vertex) return mgp_error::MGP_ERROR_VALUE_CONVERSION;
@@ -493,6 +509,10 @@ int fh_module_signature(void *module, const char *proc_name, char *buf, size_t c
   for (auto &a : it->second.opt_args) {
     if (!first) s += ", ";
     first = false;
+    if (a.required) {
+      s += a.name + " :: " + a.type->name;
+      continue;
+    }
     char num[64];
     if (a.default_value.kind == ValueKind::Int)
       snprintf(num, sizeof(num), "%lld", static_cast<long long>(a.default_value.i));
@@ -528,15 +548,20 @@ void *fh_call(void *module, const char *proc_name, void *graph_data, int n_args,
   }
   mgp_proc &proc = it->second;
   const std::string fq = m->name + "." + proc.name;
-  if (n_args < 0 || static_cast<size_t>(n_args) > proc.opt_args.size()) {
-    res_out->error = "'" + fq + "' requires between 0 and " + std::to_string(proc.opt_args.size()) + " arguments.";
+  size_t n_required = 0;
+  for (auto &a : proc.opt_args) n_required += a.required;
+  if (n_args < 0 || static_cast<size_t>(n_args) > proc.opt_args.size() || static_cast<size_t>(n_args) < n_required) {
+    res_out->error = "'" + fq + "' requires between " + std::to_string(n_required) + " and " +
+                     std::to_string(proc.opt_args.size()) + " arguments.";
     return res_out;
   }
+  mgp_graph graph{static_cast<FakeGraphData *>(graph_data)};
+  std::vector<std::unique_ptr<mgp_vertex>> arg_vertices;
   mgp_list args;
   for (size_t i = 0; i < proc.opt_args.size(); ++i) {
     mgp_value v;
     if (i < static_cast<size_t>(n_args)) {
-      const ValueKind given = kinds[i] == 'i' ? ValueKind::Int : ValueKind::Double;
+      const ValueKind given = kinds[i] == 'i' ? ValueKind::Int : (kinds[i] == 'v' ? ValueKind::Vertex : ValueKind::Double);
       if (given != proc.opt_args[i].type->kind) {  // strict: an integer literal does not satisfy FLOAT
         res_out->error = "'" + fq + "' argument named '" + proc.opt_args[i].name + "' at position " +
                          std::to_string(i) + " must be of type " + proc.opt_args[i].type->name + ".";
@@ -545,12 +570,20 @@ void *fh_call(void *module, const char *proc_name, void *graph_data, int n_args,
       v.kind = given;
       v.i = ivals[i];
       v.d = dvals[i];
+      if (given == ValueKind::Vertex) {  // a NODE argument is passed by gid
+        auto found = graph.data->index_of.find(ivals[i]);
+        if (found == graph.data->index_of.end()) {
+          res_out->error = "'" + fq + "': no vertex with the given id";
+          return res_out;
+        }
+        arg_vertices.push_back(std::make_unique<mgp_vertex>(mgp_vertex{&graph, found->second, false}));
+        v.vertex = arg_vertices.back().get();
+      }
     } else {
       v = proc.opt_args[i].default_value;
     }
     args.items.push_back(v);
   }
-  mgp_graph graph{static_cast<FakeGraphData *>(graph_data)};
   mgp_result result;
   result.proc = &proc;
   mgp_memory memory;
@@ -565,6 +598,7 @@ void *fh_call(void *module, const char *proc_name, void *graph_data, int n_args,
     for (size_t f = 0; f < proc.results.size(); ++f) {
       if (proc.results[f].first == "node") node = row->fields[f].i;
       if (proc.results[f].first == "rank") rank = row->fields[f].d;
+      if (proc.results[f].first == "distance") rank = static_cast<double>(row->fields[f].i);  // INTEGER result column
     }
     res_out->nodes.push_back(node);
     res_out->ranks.push_back(rank);

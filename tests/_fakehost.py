@@ -46,6 +46,16 @@ def host():
     return _host
 
 
+BFS_MODULE_SO = os.path.join(REPO, "memgraph_b200", "_build", "gpu_bfs.so")
+
+
+class Node:
+    """A NODE argument, passed to the procedure by the vertex's gid."""
+
+    def __init__(self, gid):
+        self.gid = int(gid)
+
+
 class ProcedureError(RuntimeError):
     """What the engine raises as QueryRuntimeException("<module>.<proc>: <msg>")."""
 
@@ -99,8 +109,10 @@ class Module:
     def call(self, graph, *args, proc="get"):
         """args: Python ints are INTEGER literals, floats are FLOAT literals (strictly typed).
         Returns (node_gids, ranks) in emission order."""
-        kinds = "".join("i" if isinstance(a, (int, np.integer)) and not isinstance(a, bool) else "d" for a in args)
-        iv = np.array([int(a) if k == "i" else 0 for a, k in zip(args, kinds)] + [0], dtype=np.int64)
+        kinds = "".join("v" if isinstance(a, Node) else
+                        ("i" if isinstance(a, (int, np.integer)) and not isinstance(a, bool) else "d") for a in args)
+        iv = np.array([a.gid if k == "v" else (int(a) if k == "i" else 0) for a, k in zip(args, kinds)] + [0],
+                      dtype=np.int64)
         dv = np.array([float(a) if k == "d" else 0.0 for a, k in zip(args, kinds)] + [0.0], dtype=np.float64)
         r = host().fh_call(self.h, proc.encode(), graph.h, len(args), kinds.encode(), iv.ctypes.data, dv.ctypes.data)
         try:
