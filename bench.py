@@ -165,7 +165,21 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    res = cpu_reference_run(args.cpu_scale, max(1, args.steps), max(0, args.warmup))
+    # Bounded sample: the reference's cost per call grows like threads x N (every iteration merges one full-length
+    # vector per thread on the main thread) -- 36 s per call at scale-22 on a 128-thread host.  Calibrate on a
+    # small graph, then take the largest scale <= --cpu-scale that keeps (steps + warmup) calls within ~150 s.
+    calls = max(1, args.steps) + max(0, args.warmup)
+    probe_scale = min(18, args.cpu_scale)
+    probe = cpu_reference_run(probe_scale, 1, 0)
+    per_call_s = probe["ms_per_step"] / 1e3
+    scale = probe_scale
+    while scale < args.cpu_scale and per_call_s * 2 * calls <= 150.0:
+        scale += 1
+        per_call_s *= 2
+    log(f"reference arm: probe scale-{probe_scale} {probe['ms_per_step']:.0f} ms/call -> sample scale-{scale} "
+        f"(~{per_call_s:.1f} s/call x {calls} calls)")
+    res = probe if (scale == probe_scale and calls == 1) else cpu_reference_run(scale, max(1, args.steps), max(0, args.warmup))
+    args.cpu_scale = scale
     line = {
         "impl": "reference", "metric": "pagerank_edges_per_second", "value": res["value"], "unit": "edges/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
