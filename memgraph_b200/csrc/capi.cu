@@ -360,7 +360,9 @@ int mgb200_pagerank_run_partition(mgb200_graph *h, const mgb200_run_params *para
     double *d_out = rank_out;
     uint32_t *d_vtx = vertex_out;
     if (!params->rank_out_on_device) {
-      MGB_CUDA(cudaMalloc(&d_out, g.local_rows * sizeof(double)));
+      // staging buffer kept for the handle's life (sized n in the single-partition path, local_rows here)
+      if (!g.out_stage) MGB_CUDA(cudaMalloc(&g.out_stage, std::max<uint64_t>(g.local_rows, g.part_world == 1 ? g.n : 0) * sizeof(double)));
+      d_out = g.out_stage;
       d_vtx = nullptr;
     }
     rc = launch_write_ranks_local(g, d_out, d_vtx);
@@ -374,7 +376,6 @@ int mgb200_pagerank_run_partition(mgb200_graph *h, const mgb200_run_params *para
     }
     e = cudaStreamSynchronize(g.stream);
     if (!rc && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
-    if (!params->rank_out_on_device) cudaFree(d_out);
     if (rc) return rc;
   }
   if (stats_out) *stats_out = stats;
