@@ -138,6 +138,12 @@ int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint6
 
 #define MGB200_IPC_HANDLE_BYTES 64
 
+/* Which global labels partition `part_rank` of `part_world` owns for an n-vertex graph: vertices sorted by degree are
+ * dealt round-robin, each owner's share becomes one contiguous label range [first_label, first_label + rows).  Host-only
+ * arithmetic (no device needed). */
+int mgb200_partition_range(uint64_t n, uint32_t part_world, uint32_t part_rank, uint64_t *first_label_out,
+                           uint64_t *rows_out);
+
 /* Exports this partition's exchange window (contribution buffers + flag page) as a CUDA IPC
  * handle, for a peer PROCESS to open. */
 int mgb200_graph_export_window(mgb200_graph *g, void *ipc_handle_out /* MGB200_IPC_HANDLE_BYTES */);

@@ -492,6 +492,19 @@ int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint6
   return MGB200_OK;
 }
 
+int mgb200_partition_range(uint64_t n, uint32_t part_world, uint32_t part_rank, uint64_t *first_label_out,
+                           uint64_t *rows_out) {
+  if (part_world == 0 || part_world > static_cast<uint32_t>(kMaxPeers) || part_rank >= part_world) {
+    set_error("invalid partition: rank " + std::to_string(part_rank) + " of " + std::to_string(part_world));
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  // same arithmetic as Dealer in graph_build.cu: sorted position p belongs to owner p % world
+  const uint64_t base = n / part_world, extra = n % part_world;
+  if (first_label_out) *first_label_out = static_cast<uint64_t>(part_rank) * base + std::min<uint64_t>(part_rank, extra);
+  if (rows_out) *rows_out = base + (part_rank < extra ? 1 : 0);
+  return MGB200_OK;
+}
+
 // ---- multi-GPU wiring ---------------------------------------------------------------------------------
 
 int mgb200_graph_export_window(mgb200_graph *h, void *ipc_handle_out) {

@@ -114,6 +114,15 @@ struct Graph {
   cudaEvent_t fork_evs[kMaxChunks] = {};
   cudaEvent_t join_ev = nullptr;
   bool overlap_epilogue = true;
+  bool stream_attr_set = false;
+  struct Tunables {  // environment, read once per graph in build_graph()
+    uint64_t l2_hot_mb = 64;     // MGB200_L2_HOT_MB: evict-last window of the gathered vector (64 = effective L2, l2_bench)
+    long l1_hot_k = 16;          // MGB200_L1_HOT_K: hottest labels (x1024) allowed to allocate in L1; <0 = no L1 hints
+    bool multi_aware = true;     // MGB200_MULTI_AWARE=0: legacy "global label prefix is hot" on every partition
+    bool stream_kernel = false;  // MGB200_SELL_KERNEL=stream
+    int sell_chunks = 1;         // MGB200_SELL_CHUNKS
+    unsigned long long barrier_timeout_ms = 20000;  // MGB200_BARRIER_TIMEOUT_MS
+  } tun;
   // optional per-launch timing: an event pair around every kernel of the first kMaxTimedLaunches iterations
   static constexpr int kMaxTimedLaunches = 64;
   static constexpr int kClasses = 6;

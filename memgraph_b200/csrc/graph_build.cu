@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <cub/cub.cuh>
 #include <vector>
 
@@ -342,6 +343,15 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   {
     const char *s = getenv("MGB200_OVERLAP_EPILOGUE");
     g.overlap_epilogue = !(s && s[0] == '0');
+    if ((s = getenv("MGB200_L2_HOT_MB")) != nullptr) g.tun.l2_hot_mb = static_cast<uint64_t>(std::max(0l, strtol(s, nullptr, 10)));
+    if ((s = getenv("MGB200_L1_HOT_K")) != nullptr) g.tun.l1_hot_k = strtol(s, nullptr, 10);
+    if ((s = getenv("MGB200_MULTI_AWARE")) != nullptr) g.tun.multi_aware = s[0] != '0';
+    if ((s = getenv("MGB200_SELL_KERNEL")) != nullptr) g.tun.stream_kernel = strcmp(s, "stream") == 0;
+    if ((s = getenv("MGB200_SELL_CHUNKS")) != nullptr) g.tun.sell_chunks = std::max(1, atoi(s));
+    if ((s = getenv("MGB200_BARRIER_TIMEOUT_MS")) != nullptr) {
+      const unsigned long long ms = strtoull(s, nullptr, 10);
+      if (ms) g.tun.barrier_timeout_ms = ms;
+    }
   }
   for (auto &e : g.ev) MGB_CUDA(cudaEventCreate(&e));
   cudaStream_t st = g.stream;

@@ -659,58 +659,23 @@ RowEpilogue make_epilogue(const Graph &g, uint64_t it, const IterateConfig &cfg)
   return ep;
 }
 
+// Tunables are read from the environment once per graph (graph_build.cu, Graph::tun) -- no process-wide statics,
+// so concurrent calls from several sessions never race on them.
 GatherWindow make_window(const Graph &g) {
-  static long hot_mb = -1;
-  if (hot_mb < 0) {
-    const char *s = getenv("MGB200_L2_HOT_MB");
-    hot_mb = s ? strtol(s, nullptr, 10) : 64;  // effective L2 capacity for random gathers on B200 (l2_bench)
-    if (hot_mb < 0) hot_mb = 0;
-  }
+  const uint64_t hot_mb = g.tun.l2_hot_mb;
   const uint64_t total = std::min<uint64_t>((g.n + 1) * sizeof(double), 0xFFFFFF00ull);
   GatherWindow w{};
   w.total_bytes = static_cast<uint32_t>(total);
-  w.hot_bytes = static_cast<uint32_t>(std::min<uint64_t>(total, static_cast<uint64_t>(hot_mb) << 20));
-  static long l1_hot_k = -1;
-  if (l1_hot_k < 0) {
-    const char *s = getenv("MGB200_L1_HOT_K");  // in units of 1024 labels; 0 = every gather may allocate in L1
-    l1_hot_k = s ? strtol(s, nullptr, 10) : 16;  // sweep: profiles/r01_l1_hot_sweep.txt; negative = no L1 hints
-  }
-  static int multi_aware = -1;
-  if (multi_aware < 0) {
-    const char *s = getenv("MGB200_MULTI_AWARE");  // 0: treat the global label prefix as hot on every partition (legacy)
-    multi_aware = (s && s[0] == '0') ? 0 : 1;
-  }
+  w.hot_bytes = static_cast<uint32_t>(std::min<uint64_t>(total, hot_mb << 20));
   w.world = g.part_world;
-  const uint32_t div = multi_aware ? g.part_world : 1;
-  w.l1_hot = l1_hot_k < 0 ? kL1Plain
-                          : static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(l1_hot_k) * 1024 / div, 0xFFFFFFF0ull));
-  w.l2_hot = multi_aware ? static_cast<uint32_t>((static_cast<uint64_t>(hot_mb) << 20) / sizeof(double) / g.part_world)
-                         : 0xFFFFFFFFu;
+  const uint32_t div = g.tun.multi_aware ? g.part_world : 1;
+  w.l1_hot = g.tun.l1_hot_k < 0 ? kL1Plain
+                                : static_cast<uint32_t>(std::min<uint64_t>(
+                                      static_cast<uint64_t>(g.tun.l1_hot_k) * 1024 / div, 0xFFFFFFF0ull));
+  w.l2_hot = g.tun.multi_aware ? static_cast<uint32_t>((hot_mb << 20) / sizeof(double) / g.part_world) : 0xFFFFFFFFu;
   for (uint32_t q = 0; q < static_cast<uint32_t>(kMaxPeers); ++q)
     w.start[q] = q < g.part_world ? static_cast<uint32_t>(g.part_start[q]) : 0xFFFFFFFFu;
   return w;
-}
-
-bool use_stream_kernel() {
-  static int cached = -1;
-  if (cached < 0) {
-    // "rows" (default): warp-per-slice loop, gathers through LDG; "stream": TMA index ring + LDGSTS gathers
-    // (sell_stream.cuh) -- correct, but measured slower (3.4 vs 2.4 ms at scale-26, profiles/r01_stream_vs_rows.md)
-    const char *s = getenv("MGB200_SELL_KERNEL");
-    cached = (s && strcmp(s, "stream") == 0) ? 1 : 0;
-  }
-  return cached == 1;
-}
-
-unsigned long long barrier_timeout_ns() {
-  static unsigned long long cached = 0;
-  if (!cached) {
-    const char *s = getenv("MGB200_BARRIER_TIMEOUT_MS");
-    unsigned long long ms = s ? strtoull(s, nullptr, 10) : 20000ull;
-    if (ms == 0) ms = 20000ull;
-    cached = ms * 1000000ull;
-  }
-  return cached;
 }
 
 BarrierArgs make_barrier(const Graph &g) {
@@ -720,7 +685,7 @@ BarrierArgs make_barrier(const Graph &g) {
   b.rank = static_cast<int>(g.part_rank);
   b.world = static_cast<int>(g.part_world);
   for (int q = 0; q < kMaxPeers; ++q) b.peer[q] = q < b.world ? g.peers.flags[q] : nullptr;
-  b.timeout_ns = barrier_timeout_ns();
+  b.timeout_ns = g.tun.barrier_timeout_ms * 1000000ull;
   return b;
 }
 
@@ -796,26 +761,20 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     // The SELL class can run as `chunks` launches over contiguous slice ranges of ~equal column counts, with the
     // epilogue (+ NVLink push) of chunk c forked to the side stream as soon as chunk c's sums exist
     // (MGB200_SELL_CHUNKS).  Default 1: at 2/4/8 GPUs the extra launches cost more than the earlier push saves.
-    const bool stream_kernel = use_stream_kernel() && g.sell_items > 0;
-    int chunks = 1;
-    if (!stream_kernel && g.overlap_epilogue && !g.sell_item_begin_host.empty()) {
-      static int env_chunks = -1;
-      if (env_chunks < 0) {
-        const char *e = getenv("MGB200_SELL_CHUNKS");
-        env_chunks = e ? atoi(e) : 0;
-      }
-      chunks = env_chunks > 0 ? env_chunks : 1;  // measured: no gain from chunking at 2/4/8 GPUs (profiles/r01_multi_gpu.md)
-      chunks = std::max(1, std::min(chunks, Graph::kMaxChunks));
-    }
+    // "rows" (default): warp-per-slice loop, gathers through LDG; "stream": TMA index ring + LDGSTS gathers
+    // (sell_stream.cuh) -- correct, but measured slower (3.4 vs 2.4 ms at scale-26, profiles/r01_stream_vs_rows.md)
+    const bool stream_kernel = g.tun.stream_kernel && g.sell_items > 0;
+    int chunks = 1;  // measured: no gain from chunking at 2/4/8 GPUs (profiles/r01_multi_gpu.md)
+    if (!stream_kernel && g.overlap_epilogue && !g.sell_item_begin_host.empty())
+      chunks = std::max(1, std::min(g.tun.sell_chunks, Graph::kMaxChunks));
     cudaStream_t es = g.overlap_epilogue ? g.stream2 : g.stream;
     const int egrid_full = grid_for(g, reinterpret_cast<const void *>(sell_epilogue_kernel));
     MGB_CUDA(tick(Graph::kClsSell, 0, g.stream));
     if (stream_kernel) {
-      static bool attr_set = false;
-      if (!attr_set) {
+      if (!g.stream_attr_set) {  // per device, so per graph handle
         MGB_CUDA(cudaFuncSetAttribute(sell_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kStreamSmemBytes));
-        attr_set = true;
+        g.stream_attr_set = true;
       }
       SellStreamArgs t{};
       t.colbase = g.sell_colbase;

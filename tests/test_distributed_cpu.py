@@ -59,8 +59,20 @@ def test_two_rank_plumbing_gloo(tmp_path, n):
 
 
 def test_partition_rows_cover_all_vertices():
+    """Python plan == the library's partition arithmetic (host-only C ABI call), ranges tile [0, n) in rank order."""
+    import ctypes
+    from memgraph_b200 import _native as N
     from memgraph_b200.distributed import partition_rows
-    for n in [0, 1, 7, 8, 1000003]:
+    lib = N.lib()
+    for n in [0, 1, 7, 8, 1000003, 2**26]:
         for world in [1, 2, 3, 8]:
             rows = partition_rows(n, world)
             assert sum(rows) == n and max(rows) - min(rows) <= 1
+            nxt = 0
+            for q in range(world):
+                first, cnt = ctypes.c_uint64(), ctypes.c_uint64()
+                assert lib.mgb200_partition_range(n, world, q, ctypes.byref(first), ctypes.byref(cnt)) == 0
+                assert (first.value, cnt.value) == (nxt, rows[q])
+                nxt += cnt.value
+            assert nxt == n
+    assert lib.mgb200_partition_range(10, 9, 0, None, None) != 0 and b"invalid partition" in lib.mgb200_last_error()
