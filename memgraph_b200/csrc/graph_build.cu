@@ -346,6 +346,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     if ((s = getenv("MGB200_L2_HOT_MB")) != nullptr) g.tun.l2_hot_mb = static_cast<uint64_t>(std::max(0l, strtol(s, nullptr, 10)));
     if ((s = getenv("MGB200_L1_HOT_K")) != nullptr) g.tun.l1_hot_k = strtol(s, nullptr, 10);
     if ((s = getenv("MGB200_MULTI_AWARE")) != nullptr) g.tun.multi_aware = s[0] != '0';
+    if ((s = getenv("MGB200_FORCE_MULTI_PATH")) != nullptr) g.tun.force_multi_path = s[0] == '1';
     if ((s = getenv("MGB200_SELL_KERNEL")) != nullptr) g.tun.stream_kernel = strcmp(s, "stream") == 0;
     if ((s = getenv("MGB200_SELL_CHUNKS")) != nullptr) g.tun.sell_chunks = std::max(1, atoi(s));
     if ((s = getenv("MGB200_BARRIER_TIMEOUT_MS")) != nullptr) {

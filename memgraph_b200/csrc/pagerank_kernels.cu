@@ -84,6 +84,7 @@ struct GatherWindow {
   uint32_t l1_hot;       // local indices below this may allocate in L1
   uint32_t l2_hot;       // local indices below this are L2 evict_last (multi-partition form)
   uint32_t world;        // number of partitions
+  uint32_t multi_path;   // 1: per-load hot/cold selection by local index (kernels instantiated with kMulti = true)
   uint32_t start[kMaxPeers];  // first global label of every partition
 };
 constexpr uint32_t kL1Plain = 0xFFFFFFFFu;  // GatherWindow::l1_hot value meaning "no L1 hints"
@@ -94,7 +95,7 @@ struct GatherPolicy {
 __device__ __forceinline__ GatherPolicy make_gather_policy(const double *contrib_in, const GatherWindow &w) {
   GatherPolicy p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.cold));
-  if (w.world <= 1 || w.l2_hot == 0xFFFFFFFFu) {  // single partition, or partition-unaware legacy mode
+  if (!w.multi_path) {  // single partition, or partition-unaware legacy mode: one range policy over the prefix
     asm volatile("createpolicy.range.global.L2::evict_last.L2::evict_first.b64 %0, [%1], %2, %3;"
                  : "=l"(p.hot)
                  : "l"(contrib_in), "r"(w.hot_bytes), "r"(w.total_bytes));
@@ -673,6 +674,7 @@ GatherWindow make_window(const Graph &g) {
                                 : static_cast<uint32_t>(std::min<uint64_t>(
                                       static_cast<uint64_t>(g.tun.l1_hot_k) * 1024 / div, 0xFFFFFFF0ull));
   w.l2_hot = g.tun.multi_aware ? static_cast<uint32_t>((hot_mb << 20) / sizeof(double) / g.part_world) : 0xFFFFFFFFu;
+  w.multi_path = (g.tun.multi_aware && (g.part_world > 1 || g.tun.force_multi_path)) ? 1u : 0u;
   for (uint32_t q = 0; q < static_cast<uint32_t>(kMaxPeers); ++q)
     w.start[q] = q < g.part_world ? static_cast<uint32_t>(g.part_start[q]) : 0xFFFFFFFFu;
   return w;
@@ -790,7 +792,7 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
       const int sgrid = static_cast<int>(std::min<uint64_t>(g.sm_count, ceil_div(g.sell_items, kStreamWarps)));
       sell_stream_kernel<<<sgrid, kStreamThreads, kStreamSmemBytes, g.stream>>>(t);
     }
-    const bool multi = s.window.world > 1 && s.window.l2_hot != 0xFFFFFFFFu;
+    const bool multi = s.window.multi_path != 0;
     const void *fn = multi ? reinterpret_cast<const void *>(sell_rows_kernel<true>)
                            : reinterpret_cast<const void *>(sell_rows_kernel<false>);
     const int grid_full = grid_for(g, fn);
@@ -845,7 +847,7 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     h.window = make_window(g);
     h.state = g.state;
     h.ep = ep;
-    const bool multi = h.window.world > 1 && h.window.l2_hot != 0xFFFFFFFFu;
+    const bool multi = h.window.multi_path != 0;
     const void *hfn = multi ? reinterpret_cast<const void *>(heavy_segments_kernel<true>)
                             : reinterpret_cast<const void *>(heavy_segments_kernel<false>);
     int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_for(g, hfn)), ceil_div(g.n_seg, kWarpsPerBlock)));
