@@ -25,6 +25,11 @@ namespace mgb200 {
 
 constexpr int kMaxPeers = 8;
 constexpr int kSliceRows = 32;
+// When Graph::idx_flagged, a stored source index (heavy_idx / sell_idx) carries the hotness of its label:
+constexpr uint32_t kIdxL2Hot = 0x80000000u;     // keep in L2 (evict_last), else evict_first
+constexpr uint32_t kIdxL1Hot = 0x40000000u;     // may allocate in L1, else bypass
+constexpr uint32_t kIdxLabelMask = 0x3FFFFFFFu; // the label itself: flagged graphs have n < 2^30
+constexpr uint32_t kNoL1Hints = 0xFFFFFFFFu;    // l1_hot_labels() when MGB200_L1_HOT_K < 0
 
 // Written by iteration kernels, read by the host between batches (plain device memory).
 struct IterState {
@@ -75,7 +80,7 @@ struct Graph {
   // heavy class
   uint64_t heavy_edges = 0;
   uint64_t *heavy_ptr = nullptr;  // [n_heavy + 1]
-  uint32_t *heavy_idx = nullptr;  // [heavy_edges] source labels, ascending inside a row
+  uint32_t *heavy_idx = nullptr;  // [heavy_edges] source labels (+ hot flags if idx_flagged), ascending inside a row
   uint64_t n_seg = 0;
   uint32_t *seg_row = nullptr;    // [n_seg] local heavy row
   uint64_t *seg_begin = nullptr;  // [n_seg] first edge
@@ -86,7 +91,8 @@ struct Graph {
   uint64_t n_slices = 0;
   uint64_t sell_entries = 0;
   uint64_t *sell_colbase = nullptr;  // [n_slices + 1] in units of 32-entry columns
-  uint32_t *sell_idx = nullptr;      // [sell_entries] source labels, pad = n
+  uint32_t *sell_idx = nullptr;      // [sell_entries] source labels (+ hot flags if idx_flagged), pad = n
+  bool idx_flagged = false;          // bits 31/30 of every stored index = L2-hot / L1-hot (graph_build.cu IndexFlags)
   double *sell_sums = nullptr;       // [n_sell] per-row gathered sums of the current iteration
   uint32_t sell_items = 0;           // work items of the streaming kernel: contiguous slice runs, ~equal columns
   uint64_t *sell_item_begin = nullptr;  // [sell_items + 1] first slice of each item
@@ -121,9 +127,23 @@ struct Graph {
     bool multi_aware = true;     // MGB200_MULTI_AWARE=0: legacy "global label prefix is hot" on every partition
     bool force_multi_path = false;  // MGB200_FORCE_MULTI_PATH=1: run the multi-partition gather code on one GPU (measurement)
     bool stream_kernel = false;  // MGB200_SELL_KERNEL=stream
+    int idx_flags = -1;          // MGB200_IDX_FLAGS: 1 bake hotness into the indices, 0 never, -1 (default) see build_graph
     int sell_chunks = 1;         // MGB200_SELL_CHUNKS
     unsigned long long barrier_timeout_ms = 20000;  // MGB200_BARRIER_TIMEOUT_MS
   } tun;
+  // hot thresholds in LOCAL label units (label - first label of the owning partition); one definition for the
+  // build-time index flags and the run-time gather window
+  uint32_t hot_divisor() const { return tun.multi_aware ? part_world : 1u; }
+  uint32_t l1_hot_labels() const {
+    if (tun.l1_hot_k < 0) return kNoL1Hints;
+    const uint64_t v = static_cast<uint64_t>(tun.l1_hot_k) * 1024 / hot_divisor();
+    return static_cast<uint32_t>(v < 0xFFFFFFF0ull ? v : 0xFFFFFFF0ull);
+  }
+  uint32_t l2_hot_labels() const {
+    if (!tun.multi_aware) return 0xFFFFFFFFu;
+    const uint64_t v = (tun.l2_hot_mb << 20) / sizeof(double) / part_world;
+    return static_cast<uint32_t>(v < 0xFFFFFFFFull ? v : 0xFFFFFFFFull);
+  }
   // optional per-launch timing: an event pair around every kernel of the first kMaxTimedLaunches iterations
   static constexpr int kMaxTimedLaunches = 64;
   static constexpr int kClasses = 6;

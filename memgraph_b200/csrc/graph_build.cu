@@ -157,10 +157,30 @@ struct U32ToU64 {
 
 // ---- heavy class ---------------------------------------------------------------------------------------
 
-__global__ void low32_kernel(uint64_t count, const uint64_t *key, uint32_t *out) {
+// Hotness of a source label (core.hpp kIdxL2Hot / kIdxL1Hot), decided once per stored index instead of once per
+// gather per iteration: local = label - first label of the owning partition (the dealt labelling gives every
+// partition's range its own hottest-first order), compared with the thresholds the gather window uses.
+struct IndexFlags {
+  Dealer deal;
+  uint32_t l1_hot, l2_hot;  // Graph::l1_hot_labels() (kNoL1Hints -> no L1 flag is ever read), l2_hot_labels()
+  uint32_t enabled;
+  __device__ uint32_t operator()(uint32_t label) const {
+    if (!enabled) return label;
+    if (label >= deal.n) return label | kIdxL2Hot | kIdxL1Hot;  // the pad slot: one address, read by every slice
+    uint32_t s0 = 0;
+    for (uint32_t q = 1; q < deal.world; ++q) {
+      const uint32_t s = static_cast<uint32_t>(deal.start(q));
+      if (label >= s) s0 = s;
+    }
+    const uint32_t local = label - s0;
+    return label | (local < l2_hot ? kIdxL2Hot : 0u) | (l1_hot != kNoL1Hints && local < l1_hot ? kIdxL1Hot : 0u);
+  }
+};
+
+__global__ void low32_kernel(uint64_t count, const uint64_t *key, IndexFlags flags, uint32_t *out) {
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   for (uint64_t e = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < count; e += stride)
-    out[e] = static_cast<uint32_t>(key[e]);
+    out[e] = flags(static_cast<uint32_t>(key[e]));
 }
 
 struct SegCount {
@@ -193,7 +213,8 @@ __global__ void slice_width_kernel(uint64_t n_slices, const uint32_t *indeg_loca
 }
 
 __global__ void sell_fill_kernel(uint64_t n_slices, uint64_t first_row, uint64_t end_row, const uint64_t *row_ptr,
-                                 const uint64_t *key, const uint64_t *colbase, uint32_t pad, uint32_t *sell_idx) {
+                                 const uint64_t *key, const uint64_t *colbase, uint32_t pad, IndexFlags flags,
+                                 uint32_t *sell_idx) {
   const int lane = threadIdx.x & 31;
   const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5);
   for (uint64_t s = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_slices;
@@ -209,7 +230,7 @@ __global__ void sell_fill_kernel(uint64_t n_slices, uint64_t first_row, uint64_t
     }
     uint32_t *dst = sell_idx + c0 * kSliceRows + lane;
     for (uint32_t k = 0; k < width; ++k)
-      dst[static_cast<size_t>(k) * kSliceRows] = k < deg ? static_cast<uint32_t>(key[e0 + k]) : pad;
+      dst[static_cast<size_t>(k) * kSliceRows] = flags(k < deg ? static_cast<uint32_t>(key[e0 + k]) : pad);
   }
 }
 
@@ -348,6 +369,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     if ((s = getenv("MGB200_MULTI_AWARE")) != nullptr) g.tun.multi_aware = s[0] != '0';
     if ((s = getenv("MGB200_FORCE_MULTI_PATH")) != nullptr) g.tun.force_multi_path = s[0] == '1';
     if ((s = getenv("MGB200_SELL_KERNEL")) != nullptr) g.tun.stream_kernel = strcmp(s, "stream") == 0;
+    if ((s = getenv("MGB200_IDX_FLAGS")) != nullptr) g.tun.idx_flags = atoi(s);
     if ((s = getenv("MGB200_SELL_CHUNKS")) != nullptr) g.tun.sell_chunks = std::max(1, atoi(s));
     if ((s = getenv("MGB200_BARRIER_TIMEOUT_MS")) != nullptr) {
       const unsigned long long ms = strtoull(s, nullptr, 10);
@@ -363,6 +385,12 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   MGB_CUDA(cudaEventRecord(g.ev[0], st));
   Scratch tmp;
   const Dealer deal{n, g.part_world};
+  // Hot flags in the stored indices replace the per-gather owner lookup on several partitions (default there);
+  // on one partition the range policy already costs nothing per gather, so flags are opt-in (MGB200_IDX_FLAGS=1).
+  // They need two index bits (n < 2^30) and partition-aware thresholds; the TMA stream kernel reads raw indices.
+  g.idx_flagged = (g.tun.idx_flags > 0 || (g.tun.idx_flags < 0 && g.part_world > 1)) && g.tun.multi_aware &&
+                  !g.tun.stream_kernel && n < (1ull << 30);
+  const IndexFlags idx_flags{deal, g.l1_hot_labels(), g.l2_hot_labels(), g.idx_flagged ? 1u : 0u};
   g.row_lo = n ? deal.start(g.part_rank) : 0;
   g.local_rows = n ? deal.count(g.part_rank) : 0;
   const uint64_t row_hi = g.row_lo + g.local_rows;
@@ -525,7 +553,8 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     MGB_CUDA(keep_alloc(g, &g.heavy_ptr, g.n_heavy + 1));
     MGB_CUDA(cudaMemcpyAsync(g.heavy_ptr, row_ptr, (g.n_heavy + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     MGB_CUDA(keep_alloc(g, &g.heavy_idx, g.heavy_edges));
-    low32_kernel<<<blocks_for(g.heavy_edges, g.sm_count), kThreads, 0, st>>>(g.heavy_edges, ekey, g.heavy_idx);
+    low32_kernel<<<blocks_for(g.heavy_edges, g.sm_count), kThreads, 0, st>>>(g.heavy_edges, ekey, idx_flags,
+                                                                                   g.heavy_idx);
     MGB_CUDA(keep_alloc(g, &g.seg_first, g.n_heavy + 1));
     {
       cub::TransformInputIterator<uint64_t, SegCount, const uint32_t *> it(indeg_local, SegCount{g.segment_edges});
@@ -575,7 +604,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     MGB_CUDA(keep_alloc(g, &g.sell_idx, g.sell_entries));
     sell_fill_kernel<<<blocks_for(g.n_slices * 32, g.sm_count), kThreads, 0, st>>>(
         g.n_slices, g.n_heavy, g.n_heavy + g.n_sell, row_ptr, ekey, g.sell_colbase, static_cast<uint32_t>(n),
-        g.sell_idx);
+        idx_flags, g.sell_idx);
     MGB_CUDA(keep_alloc(g, &g.sell_sums, g.n_sell));
     g.sell_items = env_u32("MGB200_SELL_ITEMS", static_cast<uint32_t>(g.sm_count) * 32u);
     MGB_CUDA(keep_alloc(g, &g.sell_item_begin, static_cast<uint64_t>(g.sell_items) + 1));

@@ -84,10 +84,17 @@ struct GatherWindow {
   uint32_t l1_hot;       // local indices below this may allocate in L1
   uint32_t l2_hot;       // local indices below this are L2 evict_last (multi-partition form)
   uint32_t world;        // number of partitions
-  uint32_t multi_path;   // 1: per-load hot/cold selection by local index (kernels instantiated with kMulti = true)
+  uint32_t path;         // kernel instantiation: kPathRange / kPathLookup / kPathFlags (below)
   uint32_t start[kMaxPeers];  // first global label of every partition
 };
-constexpr uint32_t kL1Plain = 0xFFFFFFFFu;  // GatherWindow::l1_hot value meaning "no L1 hints"
+constexpr uint32_t kL1Plain = kNoL1Hints;  // GatherWindow::l1_hot value meaning "no L1 hints"
+// How a gather learns whether its source is hot:
+//   kPathRange  one partition: a createpolicy.range over the prefix decides L2, `label < l1_hot` decides L1;
+//   kPathLookup P partitions, plain indices: owner found by <= 7 compare/selects per gather (costs 4.7 %,
+//               profiles/r01_multi_gpu.md), kept for graphs with >= 2^30 vertices and as the A/B baseline;
+//   kPathFlags  the hotness was computed ONCE at build time and rides in bits 31/30 of the stored index
+//               (graph_build.cu IndexFlags): two bit tests per gather, no per-partition table in the kernel.
+constexpr int kPathRange = 0, kPathLookup = 1, kPathFlags = 2;
 struct GatherPolicy {
   uint64_t hot;   // single partition: the range policy; else fractional evict_last
   uint64_t cold;  // fractional evict_first
@@ -95,7 +102,7 @@ struct GatherPolicy {
 __device__ __forceinline__ GatherPolicy make_gather_policy(const double *contrib_in, const GatherWindow &w) {
   GatherPolicy p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.cold));
-  if (!w.multi_path) {  // single partition, or partition-unaware legacy mode: one range policy over the prefix
+  if (w.path == kPathRange) {  // single partition, or partition-unaware legacy mode: one range policy over the prefix
     asm volatile("createpolicy.range.global.L2::evict_last.L2::evict_first.b64 %0, [%1], %2, %3;"
                  : "=l"(p.hot)
                  : "l"(contrib_in), "r"(w.hot_bytes), "r"(w.total_bytes));
@@ -104,26 +111,35 @@ __device__ __forceinline__ GatherPolicy make_gather_policy(const double *contrib
   }
   return p;
 }
-template <bool kMulti>
+template <int kPath, bool kSelectL2 = true>
 __device__ __forceinline__ double ld_contrib_at(const double *base, uint32_t src, const GatherPolicy &gp,
                                                 const GatherWindow &w) {
-  uint32_t local = src;
+  uint32_t label = src;
   uint64_t pol = gp.hot;
-  if (kMulti) {
+  bool l1_hot;
+  if (kPath == kPathFlags) {
+    label = src & kIdxLabelMask;
+    if (kSelectL2) pol = (src & kIdxL2Hot) ? gp.hot : gp.cold;  // else: every gather of this kernel evict_last
+    l1_hot = (src & kIdxL1Hot) != 0;
+  } else if (kPath == kPathLookup) {
     uint32_t s0 = 0;
 #pragma unroll
     for (int q = 1; q < kMaxPeers; ++q)
       if (q < static_cast<int>(w.world) && src >= w.start[q]) s0 = w.start[q];
-    local = src - s0;
+    const uint32_t local = src - s0;
     pol = local < w.l2_hot ? gp.hot : gp.cold;
+    l1_hot = local < w.l1_hot;
+  } else {
+    l1_hot = src < w.l1_hot;
   }
+  const double *p = base + label;
   double v;
   if (w.l1_hot == kL1Plain) {  // default L1 policy for every gather
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(base + src), "l"(pol));
-  } else if (local < w.l1_hot) {
-    asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(base + src), "l"(pol));
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  } else if (l1_hot) {
+    asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
   } else {
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(base + src), "l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
   }
   return v;
 }
@@ -325,7 +341,7 @@ __global__ void __launch_bounds__(kBlockThreads) sell_epilogue_kernel(uint64_t f
 #define MGB_SELL_PREFETCH 0    // 1: load the next batch of column indices before consuming the current gathers
 #endif
 
-template <bool kMulti>
+template <int kPath>
 __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_kernel(const SellArgs a) {
   if (ld_volatile_int(&a.state->done)) return;
   const int lane = threadIdx.x & 31;
@@ -380,7 +396,7 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_
       for (int j = 0; j < kUnroll; ++j) src[j] = ld_index(p + static_cast<size_t>(k + j) * kSliceRows, pol);
 #endif
 #pragma unroll
-      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib_at<kMulti>(a.contrib_in, src[j], gpol, a.window);
+      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib_at<kPath>(a.contrib_in, src[j], gpol, a.window);
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) acc += v[j];  // fixed order: ascending source label
     }
@@ -392,7 +408,7 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_
         if (k + j < width) src[j] = ld_index(p + static_cast<size_t>(k + j) * kSliceRows, pol);
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j)
-        if (k + j < width) v[j] = ld_contrib_at<kMulti>(a.contrib_in, src[j], gpol, a.window);
+        if (k + j < width) v[j] = ld_contrib_at<kPath>(a.contrib_in, src[j], gpol, a.window);
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j)
         if (k + j < width) acc += v[j];
@@ -422,8 +438,15 @@ struct HeavyArgs {
   RowEpilogue ep;
 };
 
-template <bool kMulti>
-__global__ void __launch_bounds__(kBlockThreads, 8) heavy_segments_kernel(const HeavyArgs a) {
+#ifndef MGB_HEAVY_MIN_BLOCKS
+#define MGB_HEAVY_MIN_BLOCKS 8  // 32 registers: occupancy beats the 8-16 B of spill (measured, r01_multi_gpu.md)
+#endif
+#ifndef MGB_HEAVY_FLAGS_L2
+#define MGB_HEAVY_FLAGS_L2 1    // flagged indices: 1 = per-load L2 hot/cold selection, 0 = L1 flag only
+#endif
+template <int kPath>
+__global__ void __launch_bounds__(kBlockThreads, MGB_HEAVY_MIN_BLOCKS) heavy_segments_kernel(const HeavyArgs a) {
+  constexpr bool kSelL2 = MGB_HEAVY_FLAGS_L2 != 0;
   if (ld_volatile_int(&a.state->done)) return;
   const int lane = threadIdx.x & 31;
   const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * kWarpsPerBlock;
@@ -443,11 +466,12 @@ __global__ void __launch_bounds__(kBlockThreads, 8) heavy_segments_kernel(const 
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) src[j] = ld_index(a.heavy_idx + e + 32ull * j, pol);
 #pragma unroll
-      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib_at<kMulti>(a.contrib_in, src[j], gpol, a.window);
+      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib_at<kPath, kSelL2>(a.contrib_in, src[j], gpol, a.window);
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) acc += v[j];
     }
-    for (; e < e1; e += 32) acc += ld_contrib_at<kMulti>(a.contrib_in, ld_index(a.heavy_idx + e, pol), gpol, a.window);
+    for (; e < e1; e += 32)
+      acc += ld_contrib_at<kPath, kSelL2>(a.contrib_in, ld_index(a.heavy_idx + e, pol), gpol, a.window);
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(kFull, acc, o);  // fixed tree
     if (lane == 0) a.seg_partial[g] = acc;
   }
@@ -669,12 +693,11 @@ GatherWindow make_window(const Graph &g) {
   w.total_bytes = static_cast<uint32_t>(total);
   w.hot_bytes = static_cast<uint32_t>(std::min<uint64_t>(total, hot_mb << 20));
   w.world = g.part_world;
-  const uint32_t div = g.tun.multi_aware ? g.part_world : 1;
-  w.l1_hot = g.tun.l1_hot_k < 0 ? kL1Plain
-                                : static_cast<uint32_t>(std::min<uint64_t>(
-                                      static_cast<uint64_t>(g.tun.l1_hot_k) * 1024 / div, 0xFFFFFFF0ull));
-  w.l2_hot = g.tun.multi_aware ? static_cast<uint32_t>((hot_mb << 20) / sizeof(double) / g.part_world) : 0xFFFFFFFFu;
-  w.multi_path = (g.tun.multi_aware && (g.part_world > 1 || g.tun.force_multi_path)) ? 1u : 0u;
+  w.l1_hot = g.l1_hot_labels();
+  w.l2_hot = g.l2_hot_labels();
+  w.path = g.idx_flagged ? kPathFlags
+           : (g.tun.multi_aware && (g.part_world > 1 || g.tun.force_multi_path)) ? kPathLookup
+                                                                                 : kPathRange;
   for (uint32_t q = 0; q < static_cast<uint32_t>(kMaxPeers); ++q)
     w.start[q] = q < g.part_world ? static_cast<uint32_t>(g.part_start[q]) : 0xFFFFFFFFu;
   return w;
@@ -792,9 +815,10 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
       const int sgrid = static_cast<int>(std::min<uint64_t>(g.sm_count, ceil_div(g.sell_items, kStreamWarps)));
       sell_stream_kernel<<<sgrid, kStreamThreads, kStreamSmemBytes, g.stream>>>(t);
     }
-    const bool multi = s.window.multi_path != 0;
-    const void *fn = multi ? reinterpret_cast<const void *>(sell_rows_kernel<true>)
-                           : reinterpret_cast<const void *>(sell_rows_kernel<false>);
+    void (*const sell_fn)(SellArgs) = s.window.path == kPathFlags    ? sell_rows_kernel<kPathFlags>
+                                      : s.window.path == kPathLookup ? sell_rows_kernel<kPathLookup>
+                                                                     : sell_rows_kernel<kPathRange>;
+    const void *fn = reinterpret_cast<const void *>(sell_fn);
     const int grid_full = grid_for(g, fn);
     for (int c = 0; c < chunks; ++c) {
       uint64_t sb = 0, se = g.n_slices;
@@ -806,10 +830,7 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
         s.slice_begin = sb;
         s.n_slices = se - sb;
         const int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_full), ceil_div(se - sb, kWarpsPerBlock)));
-        if (multi)
-          sell_rows_kernel<true><<<grid, kBlockThreads, 0, g.stream>>>(s);
-        else
-          sell_rows_kernel<false><<<grid, kBlockThreads, 0, g.stream>>>(s);
+        sell_fn<<<grid, kBlockThreads, 0, g.stream>>>(s);
         ++launches;
       }
       if (c == chunks - 1) MGB_CUDA(tick(Graph::kClsSell, 1, g.stream));
@@ -847,15 +868,13 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     h.window = make_window(g);
     h.state = g.state;
     h.ep = ep;
-    const bool multi = h.window.multi_path != 0;
-    const void *hfn = multi ? reinterpret_cast<const void *>(heavy_segments_kernel<true>)
-                            : reinterpret_cast<const void *>(heavy_segments_kernel<false>);
+    void (*const heavy_fn)(HeavyArgs) = h.window.path == kPathFlags    ? heavy_segments_kernel<kPathFlags>
+                                        : h.window.path == kPathLookup ? heavy_segments_kernel<kPathLookup>
+                                                                       : heavy_segments_kernel<kPathRange>;
+    const void *hfn = reinterpret_cast<const void *>(heavy_fn);
     int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_for(g, hfn)), ceil_div(g.n_seg, kWarpsPerBlock)));
     MGB_CUDA(tick(Graph::kClsHeavySeg, 0, g.stream));
-    if (multi)
-      heavy_segments_kernel<true><<<grid, kBlockThreads, 0, g.stream>>>(h);
-    else
-      heavy_segments_kernel<false><<<grid, kBlockThreads, 0, g.stream>>>(h);
+    heavy_fn<<<grid, kBlockThreads, 0, g.stream>>>(h);
     MGB_CUDA(tick(Graph::kClsHeavySeg, 1, g.stream));
     grid = static_cast<int>(
         std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_finish_kernel))),

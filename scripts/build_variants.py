@@ -10,6 +10,10 @@ sys.path.insert(0, REPO)
 from memgraph_b200 import build as B  # noqa: E402
 
 VARIANTS = {
+    "hv_base": [],
+    "hv_b6": ["-DMGB_HEAVY_MIN_BLOCKS=6"],
+    "hv_l2u": ["-DMGB_HEAVY_FLAGS_L2=0"],
+    "hv_l2u_b6": ["-DMGB_HEAVY_FLAGS_L2=0", "-DMGB_HEAVY_MIN_BLOCKS=6"],
     "s_w8_i3_v4": [],
     "s_w8_i3_v6": ["-DMGB_STREAM_VALS=6"],
     "s_w8_i2_v8": ["-DMGB_STREAM_IDX_STAGES=2", "-DMGB_STREAM_VALS=8"],
