@@ -153,6 +153,27 @@ def test_rmat_small_all_row_classes(mg, oracle, monkeypatch, heavy_min, seg):
     assert np.array_equal(ranks, again)  # deterministic: fixed summation order, no float atomics
 
 
+@pytest.mark.parametrize("env", [{"MGB200_IDX_FLAGS": "1"},
+                                 {"MGB200_IDX_FLAGS": "0", "MGB200_FORCE_MULTI_PATH": "1"},
+                                 {"MGB200_L1_HOT_K": "-1"}, {"MGB200_L2_HOT_MB": "0", "MGB200_IDX_FLAGS": "1"}])
+def test_gather_path_variants_are_bit_identical(mg, oracle, monkeypatch, env):
+    """How a gather learns its cache policy (range policy / hot flags baked into the stored index / per-gather owner
+    lookup, with or without L1 hints) must never change a single bit of the result: the flags live in index bits
+    31/30 and are masked off before addressing."""
+    scale = 13
+    n, m = 1 << scale, 16 << scale
+    f, t = mg.rmat_edges_host(scale, m, seed=7)
+    monkeypatch.setenv("MGB200_HEAVY_MIN_DEGREE", "64")  # a real heavy class at this size
+    base, st0 = gpu_pagerank(mg, n, f, t, max_iterations=20, stop_epsilon=0.0)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got, st1 = gpu_pagerank(mg, n, f, t, max_iterations=20, stop_epsilon=0.0)
+    assert st0.iterations == st1.iterations == 20
+    assert np.array_equal(base, got)
+    ref, _ = oracle.pagerank(n, f, t, max_iterations=20, stop_epsilon=0.0)
+    assert rel_err(got, ref) < REL_TOL
+
+
 def test_rmat_generator_host_equals_device(mg):
     from memgraph_b200 import _native as N
     lib = N.lib()
