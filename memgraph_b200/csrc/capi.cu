@@ -505,6 +505,56 @@ int mgb200_partition_range(uint64_t n, uint32_t part_world, uint32_t part_rank, 
   return MGB200_OK;
 }
 
+namespace {
+int make_row_map(uint64_t n, uint64_t heavy_rows, uint32_t part_world, int global_order, uint32_t part_rank,
+                 RowMap *map) {
+  if (part_world == 0 || part_world > static_cast<uint32_t>(kMaxPeers) || part_rank >= part_world ||
+      (global_order && heavy_rows > n)) {
+    set_error("invalid partition: rank " + std::to_string(part_rank) + " of " + std::to_string(part_world));
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  *map = RowMap{};
+  map->n = n;
+  map->heavy = global_order ? heavy_rows : 0;
+  map->world = part_world;
+  map->rank = part_rank;
+  map->global_order = global_order ? 1u : 0u;
+  map->finalize();
+  return MGB200_OK;
+}
+}  // namespace
+
+int mgb200_partition_locate(uint64_t n, uint64_t heavy_rows, uint32_t part_world, int global_order, uint64_t label,
+                            uint32_t *owner_out, uint64_t *local_row_out) {
+  RowMap map;
+  const int rc = make_row_map(n, heavy_rows, part_world, global_order, 0, &map);
+  if (rc != MGB200_OK) return rc;
+  if (label >= n) {
+    set_error("label out of range");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  if (owner_out) *owner_out = map.owner(label);
+  if (local_row_out) *local_row_out = map.local_of(label);
+  return MGB200_OK;
+}
+
+int mgb200_partition_label(uint64_t n, uint64_t heavy_rows, uint32_t part_world, int global_order, uint32_t part_rank,
+                           uint64_t local_row, uint64_t *label_out, uint64_t *rows_out) {
+  RowMap map;
+  const int rc = make_row_map(n, heavy_rows, part_world, global_order, part_rank, &map);
+  if (rc != MGB200_OK) return rc;
+  const uint64_t rows = map.local_rows(part_rank);
+  if (rows_out) *rows_out = rows;
+  if (label_out) {
+    if (local_row >= rows) {
+      set_error("local row out of range");
+      return MGB200_ERR_INVALID_ARGUMENT;
+    }
+    *label_out = map.label_of_local(local_row);
+  }
+  return MGB200_OK;
+}
+
 // ---- multi-GPU wiring ---------------------------------------------------------------------------------
 
 int mgb200_graph_export_window(mgb200_graph *h, void *ipc_handle_out) {

@@ -188,7 +188,7 @@ struct RowEpilogue {
   double damping;  // d
   double *rank;            // [local_rows]
   const uint32_t *outdeg;  // [n] by global label
-  uint64_t row_lo;
+  RowMap map;              // local row -> global label
   double *contrib_out[kMaxPeers];  // this iteration's output buffer on every partition (self included)
   int world;
 };
@@ -200,7 +200,7 @@ __device__ __forceinline__ double finish_row(const RowEpilogue &ep, uint64_t loc
   const double next = __dadd_rn(ep.base, __dmul_rn(ep.damping, acc));
   const double prev = ld_stream_f64(ep.rank + local_row, stream_pol);
   st_stream_f64(ep.rank + local_row, next, stream_pol);
-  const uint64_t label = ep.row_lo + local_row;
+  const uint64_t label = ep.map.label_of_local(local_row);
   const uint32_t od = ld_index(ep.outdeg + label, stream_pol);
   // A vertex without out-edges is never a gather source, so its contribution is never read: no division,
   // no store, and -- what matters across GPUs -- no NVLink push.  Labels are sorted by (in-degree, out-degree)
@@ -677,7 +677,7 @@ RowEpilogue make_epilogue(const Graph &g, uint64_t it, const IterateConfig &cfg)
   ep.damping = cfg.damping;
   ep.rank = g.rank;
   ep.outdeg = g.outdeg_l;
-  ep.row_lo = g.row_lo;
+  ep.map = g.map;
   ep.world = static_cast<int>(g.part_world);
   const int out_parity = static_cast<int>((it + 1) & 1ull);
   for (int q = 0; q < kMaxPeers; ++q) ep.contrib_out[q] = q < ep.world ? g.peers.contrib[out_parity][q] : nullptr;
@@ -695,9 +695,10 @@ GatherWindow make_window(const Graph &g) {
   w.world = g.part_world;
   w.l1_hot = g.l1_hot_labels();
   w.l2_hot = g.l2_hot_labels();
+  // global-order labelling: "hot" is one label prefix on every partition -> the exact single-partition code
   w.path = g.idx_flagged ? kPathFlags
-           : (g.tun.multi_aware && (g.part_world > 1 || g.tun.force_multi_path)) ? kPathLookup
-                                                                                 : kPathRange;
+           : (g.tun.multi_aware && !g.map.global_order && (g.part_world > 1 || g.tun.force_multi_path)) ? kPathLookup
+                                                                                                        : kPathRange;
   for (uint32_t q = 0; q < static_cast<uint32_t>(kMaxPeers); ++q)
     w.start[q] = q < g.part_world ? static_cast<uint32_t>(g.part_start[q]) : 0xFFFFFFFFu;
   return w;
