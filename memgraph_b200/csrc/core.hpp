@@ -144,6 +144,8 @@ struct Graph {
   uint32_t *label_of = nullptr;     // [n]  original id -> global label
   uint32_t *outdeg_l = nullptr;     // [n]  out-degree by global label
   uint32_t *local_vertex = nullptr; // [local_rows] original id of each owned row
+  uint32_t *need_mask = nullptr;    // [ceil(local_rows / 4)] one BYTE per owned row: bit q = partition q gathers this
+                                    // row's contribution (has an in-edge from it); nullptr = push to every peer
 
   // heavy class
   uint64_t heavy_edges = 0;
@@ -196,6 +198,7 @@ struct Graph {
     bool force_multi_path = false;  // MGB200_FORCE_MULTI_PATH=1: run the multi-partition gather code on one GPU (measurement)
     bool stream_kernel = false;  // MGB200_SELL_KERNEL=stream
     bool global_order = false;   // MGB200_LABELLING=global: label = global degree order, blocks of 32 dealt (RowMap)
+    bool push_mask = false;      // MGB200_PUSH_MASK=1: push a contribution only to the partitions that gather it
     int idx_flags = -1;          // MGB200_IDX_FLAGS: 1 bake hotness into the indices, 0 never, -1 (default) see build_graph
     int sell_chunks = 1;         // MGB200_SELL_CHUNKS
     unsigned long long barrier_timeout_ms = 20000;  // MGB200_BARRIER_TIMEOUT_MS

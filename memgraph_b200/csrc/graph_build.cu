@@ -152,6 +152,24 @@ __global__ void nonzero_per_partition_kernel(Dealer deal, const uint32_t *indeg_
   }
 }
 
+// Which partitions gather the contribution of an owned row?  Every partition sees the whole edge list, so this is local
+// work: edge u -> v makes owner(v) a reader of u.  At P = 8 on RMAT only 48 % of the (vertex, peer) pairs are readers
+// (scripts/push_need.py): the other half of the NVLink pushes is never looked at.
+__global__ void need_mask_kernel(uint64_t m, const uint32_t *from, const uint32_t *to, const uint32_t *label_of,
+                                 RowMap map, uint32_t *words) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t e = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < m; e += stride) {
+    const uint64_t ul = label_of[from[e]];
+    if (map.owner(ul) != map.rank) continue;
+    const uint32_t q = map.owner(label_of[to[e]]);
+    if (q == map.rank) continue;
+    const uint64_t row = map.local_of(ul);
+    const uint32_t bit = (1u << q) << ((row & 3u) * 8u);
+    uint32_t *w = words + (row >> 2);
+    if ((*reinterpret_cast<volatile uint32_t *>(w) & bit) == 0) atomicOr(w, bit);  // hubs: one atomic, then reads
+  }
+}
+
 struct U32ToU64 {
   __host__ __device__ uint64_t operator()(uint32_t v) const { return v; }
 };
@@ -336,6 +354,7 @@ void free_graph(Graph &g) {
   if (g.sell_item_begin) cudaFree(g.sell_item_begin);
   if (g.sell_sums) cudaFree(g.sell_sums);
   if (g.out_stage) cudaFree(g.out_stage);
+  if (g.need_mask) cudaFree(g.need_mask);
   void *ptrs[] = {g.label_of,  g.outdeg_l,  g.local_vertex, g.heavy_ptr,    g.heavy_idx, g.seg_row,     g.seg_begin,
                   g.seg_first, g.seg_partial, g.sell_colbase, g.sell_idx,     g.rank,      g.window,      g.state,
                   g.sum_partials};
@@ -372,6 +391,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     if ((s = getenv("MGB200_SELL_KERNEL")) != nullptr) g.tun.stream_kernel = strcmp(s, "stream") == 0;
     if ((s = getenv("MGB200_IDX_FLAGS")) != nullptr) g.tun.idx_flags = atoi(s);
     if ((s = getenv("MGB200_LABELLING")) != nullptr) g.tun.global_order = strcmp(s, "global") == 0;
+    if ((s = getenv("MGB200_PUSH_MASK")) != nullptr) g.tun.push_mask = s[0] == '1';
     if ((s = getenv("MGB200_SELL_CHUNKS")) != nullptr) g.tun.sell_chunks = std::max(1, atoi(s));
     if ((s = getenv("MGB200_BARRIER_TIMEOUT_MS")) != nullptr) {
       const unsigned long long ms = strtoull(s, nullptr, 10);
@@ -503,6 +523,12 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     gather_local_u32_kernel<<<blocks_for(g.local_rows, g.sm_count), kThreads, 0, st>>>(g.local_rows, map, indeg_l,
                                                                                       gathered);
     indeg_local = gathered;
+  }
+  if (g.tun.push_mask && g.part_world > 1 && m > 0 && g.local_rows > 0) {
+    const uint64_t words = (g.local_rows + 3) / 4;
+    MGB_CUDA(keep_alloc(g, &g.need_mask, words));
+    MGB_CUDA(cudaMemsetAsync(g.need_mask, 0, words * sizeof(uint32_t), st));
+    need_mask_kernel<<<blocks_for(m, g.sm_count), kThreads, 0, st>>>(m, d_from, d_to, g.label_of, map, g.need_mask);
   }
 
   // 4. class boundaries and local edge count

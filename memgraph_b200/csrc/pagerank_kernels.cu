@@ -191,6 +191,8 @@ struct RowEpilogue {
   RowMap map;              // local row -> global label
   double *contrib_out[kMaxPeers];  // this iteration's output buffer on every partition (self included)
   int world;
+  int self;                // this partition
+  const uint8_t *need;     // [local_rows] bit q: partition q gathers this row's contribution; nullptr = everyone
 };
 
 // rank_next = base + d * acc as two separately rounded operations, like the reference's
@@ -207,9 +209,11 @@ __device__ __forceinline__ double finish_row(const RowEpilogue &ep, uint64_t loc
   // descending, so these vertices are the contiguous tail of every in-degree class: whole warps skip.
   if (od != 0) {
     const double c = __ddiv_rn(next, static_cast<double>(od));  // :93 quotient, once per vertex
+    // push only to the partitions that have an in-edge from this vertex (graph_build.cu need_mask_kernel)
+    const uint32_t need = ep.need ? (static_cast<uint32_t>(ep.need[local_row]) | (1u << ep.self)) : 0xFFu;
 #pragma unroll
     for (int q = 0; q < kMaxPeers; ++q) {
-      if (q < ep.world) st_stream_f64(ep.contrib_out[q] + label, c, stream_pol);  // q != self: NVLink store
+      if (q < ep.world && ((need >> q) & 1u)) st_stream_f64(ep.contrib_out[q] + label, c, stream_pol);  // q != self: NVLink
     }
   }
   return fabs(next - prev);
@@ -679,6 +683,8 @@ RowEpilogue make_epilogue(const Graph &g, uint64_t it, const IterateConfig &cfg)
   ep.outdeg = g.outdeg_l;
   ep.map = g.map;
   ep.world = static_cast<int>(g.part_world);
+  ep.self = static_cast<int>(g.part_rank);
+  ep.need = reinterpret_cast<const uint8_t *>(g.need_mask);
   const int out_parity = static_cast<int>((it + 1) & 1ull);
   for (int q = 0; q < kMaxPeers; ++q) ep.contrib_out[q] = q < ep.world ? g.peers.contrib[out_parity][q] : nullptr;
   return ep;

@@ -46,12 +46,14 @@ def run_partitioned(mg, n, f, t, world, **kw):
     return out, results, infos
 
 
+@pytest.mark.parametrize("push_mask", ["0", "1"])
 @pytest.mark.parametrize("labelling", ["dealt", "global"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_partitioned_equals_oracle(world, labelling, monkeypatch):
+def test_partitioned_equals_oracle(world, labelling, push_mask, monkeypatch):
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     monkeypatch.setenv("MGB200_LABELLING", labelling)  # csrc/core.hpp RowMap: contiguous dealt ranges / global order
+    monkeypatch.setenv("MGB200_PUSH_MASK", push_mask)  # 1: contributions go only to the partitions that gather them
     import memgraph_b200 as mg
     oracle = Oracle()
     scale = 16
