@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "core.hpp"
+#include "mgb200_katz.h"
 #include "rmat.hpp"
 
 struct mgb200_graph {
@@ -490,6 +491,55 @@ int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint6
     for (size_t r = 0; r < ranks[q].size(); ++r) rank_out[vertices[q][r]] = ranks[q][r];
   if (iterations_out) *iterations_out = stats[0].iterations;
   return MGB200_OK;
+}
+
+// ---- Katz centrality (include/mgb200_katz.h; kernels in katz.cu) -----------------------------------------
+
+int mgb200_katz_run(mgb200_graph *h, double alpha, double epsilon, uint64_t max_iterations, double *centrality_out,
+                    mgb200_katz_stats *stats_out) {
+  if (!h) return MGB200_ERR_INVALID_ARGUMENT;
+  Graph &g = h->g;
+  if (g.n > 0 && !centrality_out) {
+    set_error("centrality_out is null");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  MGB_CUDA(cudaSetDevice(g.device));
+  if (g.n > 0 && !g.out_stage) MGB_CUDA(cudaMalloc(&g.out_stage, g.n * sizeof(double)));  // kept for the handle's life
+  KatzResult res;
+  int rc = katz_iterate(g, alpha, epsilon, max_iterations, g.out_stage, &res);
+  if (rc) return rc;
+  if (g.n > 0) {
+    cudaError_t e = cudaMemcpyAsync(centrality_out, g.out_stage, g.n * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(centralities D2H)", __FILE__, __LINE__);
+  }
+  if (stats_out) {
+    stats_out->iterations = res.iterations;
+    stats_out->max_out_degree = res.max_out_degree;
+    stats_out->gamma = res.gamma;
+    stats_out->iterate_ms = res.iterate_ms;
+    stats_out->kernel_launches = res.launches;
+    stats_out->tie_order_runs = res.tie_order_runs;
+  }
+  if (!res.converged) {
+    set_error("Katz centrality: max_iterations reached before the ranking separated");
+    return MGB200_KATZ_NOT_CONVERGED;
+  }
+  return MGB200_OK;
+}
+
+int mgb200_katz_centrality(uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to, double alpha,
+                           double epsilon, uint64_t max_iterations, double *centrality_out, uint64_t *iterations_out) {
+  const char *dev_env = getenv("MGB200_DEVICE");
+  const int device = dev_env ? atoi(dev_env) : 0;
+  mgb200_graph *g = nullptr;
+  int rc = mgb200_graph_create_host(device, n, m, from, to, 0, 1, &g);  // fails without a device, also for n == 0
+  if (rc) return rc;
+  mgb200_katz_stats stats{};
+  rc = mgb200_katz_run(g, alpha, epsilon, max_iterations, centrality_out, &stats);
+  mgb200_graph_destroy(g);
+  if (iterations_out) *iterations_out = stats.iterations;
+  return rc;
 }
 
 int mgb200_partition_range(uint64_t n, uint32_t part_world, uint32_t part_rank, uint64_t *first_label_out,

@@ -254,11 +254,21 @@ struct IterateConfig {
 constexpr int kSumBlocks = 1024;
 int launch_init(Graph &g, const IterateConfig &cfg);
 int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *launch_count, uint64_t *spmv_count);
+int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count);  // SELL sums + heavy partials only
 int launch_barrier(Graph &g);
 int launch_sum_and_exchange(Graph &g);
 int launch_write_ranks_original_order(Graph &g, double *d_out);                   // single partition
 int launch_write_ranks_local(Graph &g, double *d_rank_out, uint32_t *d_vertex_out);  // partitioned
 int kernel_occupancy_report(Graph &g, char *buf, size_t cap);
+
+// katz.cu
+struct KatzResult {
+  uint64_t iterations = 0, max_out_degree = 0, launches = 0, tie_order_runs = 0;
+  double gamma = 0.0, iterate_ms = 0.0;
+  bool converged = false;
+};
+int katz_iterate(Graph &g, double alpha, double epsilon, uint64_t max_iterations, double *d_out_original_order,
+                 KatzResult *res);
 
 // rmat.cu
 int rmat_device(int device, uint32_t scale, uint64_t first_edge, uint64_t count, uint64_t seed, double a, double b,

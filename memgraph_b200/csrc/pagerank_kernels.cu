@@ -911,6 +911,60 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
   return MGB200_OK;
 }
 
+// The gather phase alone, over an arbitrary per-label vector vec_in[n + 1] (slot n must hold 0): SELL row sums into
+// g.sell_sums, heavy segment partials into g.seg_partial (summed per row by the caller in segment order).  This is
+// y = A^T x for the rows of this partition with PageRank's kernels and cache policies; other SpMV-shaped paths hang
+// their own epilogue on it (Katz: omega_i = A^T omega_{i-1}, katz.cu).  Kernels return at once while state->done is set.
+int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count) {
+  uint64_t launches = 0;
+  const GatherWindow window = make_window(g);
+  if (g.n_slices > 0) {
+    SellArgs s{};
+    s.colbase = g.sell_colbase;
+    s.idx = g.sell_idx;
+    s.slice_begin = 0;
+    s.n_slices = g.n_slices;
+    s.first_row = g.n_heavy;
+    s.end_row = g.n_heavy + g.n_sell;
+    s.contrib_in = vec_in;
+    s.window = window;
+    s.state = g.state;
+    s.sums = g.sell_sums;
+    void (*const sell_fn)(SellArgs) = window.path == kPathFlags    ? sell_rows_kernel<kPathFlags>
+                                      : window.path == kPathLookup ? sell_rows_kernel<kPathLookup>
+                                                                   : sell_rows_kernel<kPathRange>;
+    const int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_fn))),
+                                               ceil_div(g.n_slices, kWarpsPerBlock)));
+    sell_fn<<<grid, kBlockThreads, 0, g.stream>>>(s);
+    ++launches;
+  }
+  if (g.n_seg > 0) {
+    HeavyArgs h{};
+    h.heavy_ptr = g.heavy_ptr;
+    h.heavy_idx = g.heavy_idx;
+    h.seg_row = g.seg_row;
+    h.seg_begin = g.seg_begin;
+    h.seg_first = g.seg_first;
+    h.seg_partial = g.seg_partial;
+    h.n_seg = g.n_seg;
+    h.n_heavy = g.n_heavy;
+    h.segment_edges = g.segment_edges;
+    h.contrib_in = vec_in;
+    h.window = window;
+    h.state = g.state;
+    void (*const heavy_fn)(HeavyArgs) = window.path == kPathFlags    ? heavy_segments_kernel<kPathFlags>
+                                        : window.path == kPathLookup ? heavy_segments_kernel<kPathLookup>
+                                                                     : heavy_segments_kernel<kPathRange>;
+    const int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_fn))),
+                                               ceil_div(g.n_seg, kWarpsPerBlock)));
+    heavy_fn<<<grid, kBlockThreads, 0, g.stream>>>(h);
+    ++launches;
+  }
+  MGB_CUDA(cudaGetLastError());
+  if (launch_count) *launch_count += launches;
+  return MGB200_OK;
+}
+
 int launch_sum_and_exchange(Graph &g) {
   const int blocks = static_cast<int>(std::min<uint64_t>(kSumBlocks, g.local_rows ? ceil_div(g.local_rows, 4096) : 1));
   partial_sum_kernel<<<blocks, kBlockThreads, 0, g.stream>>>(g.rank, g.local_rows, g.sum_partials);
