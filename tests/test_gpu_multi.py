@@ -46,10 +46,12 @@ def run_partitioned(mg, n, f, t, world, **kw):
     return out, results, infos
 
 
+@pytest.mark.parametrize("push", ["store", "copy"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_partitioned_equals_oracle(world):
+def test_partitioned_equals_oracle(world, push, monkeypatch):
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    monkeypatch.setenv("MGB200_PUSH", push)  # copy: the exchange as peer copies on the copy engines
     import memgraph_b200 as mg
     oracle = Oracle()
     scale = 16
