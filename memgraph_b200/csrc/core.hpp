@@ -191,6 +191,11 @@ struct Graph {
   cudaEvent_t join_ev = nullptr;
   bool overlap_epilogue = true;
   bool stream_attr_set = false;
+  // MGB200_PUSH=copy: the exchange as peer copies of this partition's contiguous label slices on the copy engines
+  // (one stream per peer), instead of NVLink stores issued by the epilogue kernels
+  cudaStream_t copy_streams[kMaxPeers] = {};
+  cudaEvent_t copy_done[kMaxPeers] = {};
+  cudaEvent_t sell_ready_ev = nullptr, heavy_ready_ev = nullptr;
   struct Tunables {  // environment, read once per graph in build_graph()
     uint64_t l2_hot_mb = 64;     // MGB200_L2_HOT_MB: evict-last window of the gathered vector (64 = effective L2, l2_bench)
     long l1_hot_k = 16;          // MGB200_L1_HOT_K: hottest labels (x1024) allowed to allocate in L1; <0 = no L1 hints
@@ -199,6 +204,7 @@ struct Graph {
     bool stream_kernel = false;  // MGB200_SELL_KERNEL=stream
     bool global_order = false;   // MGB200_LABELLING=global: label = global degree order, blocks of 32 dealt (RowMap)
     bool push_mask = false;      // MGB200_PUSH_MASK=1: push a contribution only to the partitions that gather it
+    bool push_copy = false;      // MGB200_PUSH=copy (dealt contiguous ranges only)
     int idx_flags = -1;          // MGB200_IDX_FLAGS: 1 bake hotness into the indices, 0 never, -1 (default) see build_graph
     int sell_chunks = 1;         // MGB200_SELL_CHUNKS
     unsigned long long barrier_timeout_ms = 20000;  // MGB200_BARRIER_TIMEOUT_MS

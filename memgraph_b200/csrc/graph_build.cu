@@ -368,6 +368,12 @@ void free_graph(Graph &g) {
   for (auto &e : g.fork_evs)
     if (e) cudaEventDestroy(e);
   if (g.join_ev) cudaEventDestroy(g.join_ev);
+  for (auto &e : g.copy_done)
+    if (e) cudaEventDestroy(e);
+  if (g.sell_ready_ev) cudaEventDestroy(g.sell_ready_ev);
+  if (g.heavy_ready_ev) cudaEventDestroy(g.heavy_ready_ev);
+  for (auto &cs : g.copy_streams)
+    if (cs) cudaStreamDestroy(cs);
   if (g.stream2) cudaStreamDestroy(g.stream2);
   if (g.stream) cudaStreamDestroy(g.stream);
 }
@@ -381,6 +387,8 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   MGB_CUDA(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
   for (auto &e : g.fork_evs) MGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   MGB_CUDA(cudaEventCreateWithFlags(&g.join_ev, cudaEventDisableTiming));
+  MGB_CUDA(cudaEventCreateWithFlags(&g.sell_ready_ev, cudaEventDisableTiming));
+  MGB_CUDA(cudaEventCreateWithFlags(&g.heavy_ready_ev, cudaEventDisableTiming));
   {
     const char *s = getenv("MGB200_OVERLAP_EPILOGUE");
     g.overlap_epilogue = !(s && s[0] == '0');
@@ -392,6 +400,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     if ((s = getenv("MGB200_IDX_FLAGS")) != nullptr) g.tun.idx_flags = atoi(s);
     if ((s = getenv("MGB200_LABELLING")) != nullptr) g.tun.global_order = strcmp(s, "global") == 0;
     if ((s = getenv("MGB200_PUSH_MASK")) != nullptr) g.tun.push_mask = s[0] == '1';
+    if ((s = getenv("MGB200_PUSH")) != nullptr) g.tun.push_copy = strcmp(s, "copy") == 0;
     if ((s = getenv("MGB200_SELL_CHUNKS")) != nullptr) g.tun.sell_chunks = std::max(1, atoi(s));
     if ((s = getenv("MGB200_BARRIER_TIMEOUT_MS")) != nullptr) {
       const unsigned long long ms = strtoull(s, nullptr, 10);

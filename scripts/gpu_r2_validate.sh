@@ -15,4 +15,7 @@ if [ "$NG" -ge 2 ]; then
       python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 \
       bench.py --gpus $NG --quick --steps 3 --warmup 3 2>/dev/null | tee -a $O
   done; done
+  MGB200_TAG="n$NG push=copy" MGB200_PUSH=copy timeout 300 \
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus $NG --quick --steps 3 --warmup 3 2>/dev/null | tee -a $O
 fi
