@@ -350,7 +350,7 @@ int mgb200_pagerank_run_partition(mgb200_graph *h, const mgb200_run_params *para
                                   uint32_t *vertex_out, mgb200_run_stats *stats_out) {
   if (!h || !params) return MGB200_ERR_INVALID_ARGUMENT;
   Graph &g = h->g;
-  if (g.part_world > 1 && !g.peers_connected) {
+  if (g.part_world > 1 && !g.peers_connected && !g.tun.lone_partition) {
     set_error("partition is not connected to its peers (mgb200_graph_connect_peers)");
     return MGB200_ERR_COMM;
   }

@@ -204,6 +204,8 @@ struct Graph {
     bool stream_kernel = false;  // MGB200_SELL_KERNEL=stream
     bool global_order = false;   // MGB200_LABELLING=global: label = global degree order, blocks of 32 dealt (RowMap)
     bool push_mask = false;      // MGB200_PUSH_MASK=1: push a contribution only to the partitions that gather it
+    bool lone_partition = false; // MGB200_LONE_PARTITION=1 (profiling only): run ONE partition of part_world without its
+                                 // peers -- no stores to them, barrier of one; timings/ncu are real, ranks are NOT
     bool push_copy = false;      // MGB200_PUSH=copy (dealt contiguous ranges only)
     int idx_flags = -1;          // MGB200_IDX_FLAGS: 1 bake hotness into the indices, 0 never, -1 (default) see build_graph
     int sell_chunks = 1;         // MGB200_SELL_CHUNKS

@@ -687,7 +687,9 @@ RowEpilogue make_epilogue(const Graph &g, uint64_t it, const IterateConfig &cfg)
   ep.world = static_cast<int>(g.part_world);
   ep.self = static_cast<int>(g.part_rank);
   ep.need = reinterpret_cast<const uint8_t *>(g.need_mask);
-  ep.store_mask = (g.tun.push_copy && g.part_world > 1 && !g.map.global_order) ? (1u << g.part_rank) : 0xFFFFFFFFu;
+  ep.store_mask = ((g.tun.push_copy && g.part_world > 1 && !g.map.global_order) || g.tun.lone_partition)
+                      ? (1u << g.part_rank)
+                      : 0xFFFFFFFFu;
   const int out_parity = static_cast<int>((it + 1) & 1ull);
   for (int q = 0; q < kMaxPeers; ++q) ep.contrib_out[q] = q < ep.world ? g.peers.contrib[out_parity][q] : nullptr;
   return ep;
@@ -720,6 +722,11 @@ BarrierArgs make_barrier(const Graph &g) {
   b.rank = static_cast<int>(g.part_rank);
   b.world = static_cast<int>(g.part_world);
   for (int q = 0; q < kMaxPeers; ++q) b.peer[q] = q < b.world ? g.peers.flags[q] : nullptr;
+  if (g.tun.lone_partition) {  // profiling: a barrier of one over the own flag page
+    b.rank = 0;
+    b.world = 1;
+    for (int q = 0; q < kMaxPeers; ++q) b.peer[q] = q == 0 ? g.flags() : nullptr;
+  }
   b.timeout_ns = g.tun.barrier_timeout_ms * 1000000ull;
   return b;
 }
@@ -798,7 +805,7 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
   const RowEpilogue ep = make_epilogue(g, it, cfg);
   const double *contrib_in = g.contrib(static_cast<int>(it & 1ull));
   uint64_t launches = 0;
-  const bool push_copy = g.tun.push_copy && g.part_world > 1 && !g.map.global_order;  // needs contiguous label ranges
+  const bool push_copy = g.tun.push_copy && g.part_world > 1 && !g.map.global_order && !g.tun.lone_partition;  // needs contiguous label ranges
   const int out_parity = static_cast<int>((it + 1) & 1ull);
   bool copy_used[kMaxPeers] = {};
   const bool timed = g.time_spmv && g.timed_launches < Graph::kMaxTimedLaunches;
