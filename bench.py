@@ -241,7 +241,13 @@ def run_b200_arm(args):
     mg.rmat_edges_device(scale, m, d_from, d_to, seed=SEED, device=device)
     gen_s = time.perf_counter() - t0
     t0 = time.perf_counter()
-    g = mg.PageRankGraph.from_device(n, m, d_from, d_to, device=device, part_rank=rank, part_world=world)
+    # profiling aid (--quick only): MGB200_LONE_WORLD=P runs partition 0 of P on ONE GPU without peers -- the per-GPU
+    # kernels of an N=P run, under ncu if wanted; ranks are meaningless, timings are not
+    lone = int(os.environ.get("MGB200_LONE_WORLD", "0")) if (args.quick and world == 1) else 0
+    if lone > 1:
+        os.environ["MGB200_LONE_PARTITION"] = "1"
+    g = mg.PageRankGraph.from_device(n, m, d_from, d_to, device=device, part_rank=rank,
+                                     part_world=lone if lone > 1 else world)
     build_wall_s = time.perf_counter() - t0
     lib.mgb200_device_free(device, d_from)
     lib.mgb200_device_free(device, d_to)
@@ -273,7 +279,7 @@ def run_b200_arm(args):
     def step_device(timed_kernel=False):
         p, _cb = make_params(ITERATIONS, DAMPING, 0.0, on_device=True, time_spmv_kernel=timed_kernel)
         st = N.RunStatsC()
-        if world == 1:
+        if world == 1 and lone <= 1:
             _check(lib.mgb200_pagerank_run(g.handle, ctypes.byref(p), d_out, ctypes.byref(st)))
         else:
             _check(lib.mgb200_pagerank_run_partition(g.handle, ctypes.byref(p), d_out, None, ctypes.byref(st)))

@@ -144,6 +144,17 @@ int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint6
 int mgb200_partition_range(uint64_t n, uint32_t part_world, uint32_t part_rank, uint64_t *first_label_out,
                            uint64_t *rows_out);
 
+/* The label <-> (owner, local row) arithmetic of both labellings, host-only (diagnostics and tests; the device code
+ * uses the same functions, csrc/core.hpp RowMap).  global_order = 0: the dealt contiguous ranges above (heavy_rows is
+ * ignored); 1: label = position in the global degree order, the first `heavy_rows` labels owned round-robin, then
+ * blocks of 32 labels owned round-robin (MGB200_LABELLING=global).
+ *   mgb200_partition_locate: label -> owning partition and its local row there;
+ *   mgb200_partition_label : (part_rank, local_row) -> label; rows_out = number of local rows of part_rank. */
+int mgb200_partition_locate(uint64_t n, uint64_t heavy_rows, uint32_t part_world, int global_order, uint64_t label,
+                            uint32_t *owner_out, uint64_t *local_row_out);
+int mgb200_partition_label(uint64_t n, uint64_t heavy_rows, uint32_t part_world, int global_order, uint32_t part_rank,
+                           uint64_t local_row, uint64_t *label_out, uint64_t *rows_out);
+
 /* Exports this partition's exchange window (contribution buffers + flag page) as a CUDA IPC
  * handle, for a peer PROCESS to open. */
 int mgb200_graph_export_window(mgb200_graph *g, void *ipc_handle_out /* MGB200_IPC_HANDLE_BYTES */);

@@ -30,6 +30,12 @@ class BfsStats(ctypes.Structure):
                 ("edges_inspected", u64), ("traverse_ms", f64), ("kernel_launches", u64)]
 
 
+class KatzStats(ctypes.Structure):
+    _fields_ = [("iterations", u64), ("max_out_degree", u64), ("gamma", f64), ("iterate_ms", f64),
+                ("kernel_launches", u64), ("tie_order_runs", u64)]
+
+
+KATZ_NOT_CONVERGED = 16
 ABORT_FN = ctypes.CFUNCTYPE(ctypes.c_int, vp)
 
 
@@ -51,6 +57,8 @@ EXPORTS = {
     "mgb200_parallel_iterative_pagerank_multi": (i32, [u64, u64, vp, vp, u64, f64, f64, u32, u32, vp, vp,
                                                        ctypes.POINTER(u64)]),
     "mgb200_partition_range": (i32, [u64, u32, u32, ctypes.POINTER(u64), ctypes.POINTER(u64)]),
+    "mgb200_partition_locate": (i32, [u64, u64, u32, i32, u64, ctypes.POINTER(u32), ctypes.POINTER(u64)]),
+    "mgb200_partition_label": (i32, [u64, u64, u32, i32, u32, u64, ctypes.POINTER(u64), ctypes.POINTER(u64)]),
     "mgb200_graph_export_window": (i32, [vp, vp]),
     "mgb200_graph_connect_peers": (i32, [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]),
     "mgb200_pagerank_run_partition": (i32, [vp, ctypes.POINTER(RunParams), vp, vp, ctypes.POINTER(RunStatsC)]),
@@ -59,6 +67,10 @@ EXPORTS = {
     "mgb200_bfs_graph_create_host": (i32, [i32, u64, u64, vp, vp, ctypes.POINTER(vp)]),
     "mgb200_bfs_graph_destroy": (None, [vp]),
     "mgb200_bfs_run": (i32, [vp, u64, i32, ctypes.c_int64, ctypes.c_int64, vp, i32, ctypes.POINTER(BfsStats)]),
+    # include/mgb200_katz.h
+    "mgb200_katz_run": (i32, [vp, f64, f64, u64, vp, ctypes.POINTER(KatzStats)]),
+    "mgb200_katz_centrality": (i32, [u64, u64, vp, vp, f64, f64, u64, vp, ctypes.POINTER(u64)]),
+    "mgb200_katz_tie_order": (i32, [u64, vp, vp]),
     "mgb200_rmat_generate_device": (i32, [i32, u32, u64, u64, u64, f64, f64, f64, vp, vp]),
     "mgb200_rmat_generate_host": (i32, [u32, u64, u64, u64, f64, f64, f64, vp, vp]),
     "mgb200_device_malloc": (i32, [i32, ctypes.c_size_t, ctypes.POINTER(vp)]),

@@ -28,15 +28,17 @@ NVCC_FLAGS = [
     "-I", INCLUDE, "-I", CSRC,
     "-diag-suppress", "1444",  # cub::TransformInputIterator deprecation notice
 ]
-CUDA_SOURCES = ["pagerank_kernels.cu", "graph_build.cu", "capi.cu", "bfs.cu"]
+CUDA_SOURCES = ["pagerank_kernels.cu", "graph_build.cu", "capi.cu", "bfs.cu", "katz.cu"]
 HEADERS = [os.path.join(CSRC, "core.hpp"), os.path.join(CSRC, "rmat.hpp"), os.path.join(CSRC, "sell_stream.cuh"),
            os.path.join(INCLUDE, "mgb200_pagerank.h"), os.path.join(INCLUDE, "mgb200_bfs.h"),
+           os.path.join(INCLUDE, "mgb200_katz.h"), os.path.join(CSRC, "katz_heap.hpp"),
            os.path.join(INCLUDE, "mgp_abi.h"), os.path.join(CSRC, "mgp_module_common.hpp")]
 
 CORE_LIB = os.path.join(OUT, "libmgb200_pagerank.so")
 MODULE_LIB = os.path.join(OUT, "pagerank.so")
 FAKE_HOST_LIB = os.path.join(OUT, "libmgp_fake_host.so")
 BFS_MODULE_LIB = os.path.join(OUT, "gpu_bfs.so")
+KATZ_MODULE_LIB = os.path.join(OUT, "katz_centrality.so")
 
 
 def _newer(target, deps):
@@ -99,6 +101,18 @@ def build_bfs_module(objs, verbose=False):
         _run([NVCC, "-shared", "-cudart", "static", "-o", BFS_MODULE_LIB, obj] + objs)
 
 
+def build_katz_module(objs, verbose=False):
+    """katz_centrality.so: static Katz centrality behind the reference module's name and signature."""
+    src = os.path.join(CSRC, "katz_centrality_module.cpp")
+    obj = os.path.join(OUT, "katz_centrality_module.o")
+    if _newer(obj, [src] + HEADERS):
+        if verbose:
+            print("g++ katz_centrality_module.cpp", flush=True)
+        _run([CXX, "-std=c++20", "-O2", "-fPIC", "-fvisibility=hidden", "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj])
+    if _newer(KATZ_MODULE_LIB, objs + [obj]):
+        _run([NVCC, "-shared", "-cudart", "static", "-o", KATZ_MODULE_LIB, obj] + objs)
+
+
 def build_fake_host(verbose=False):
     src = os.path.join(CSRC, "mgp_fake_host.cpp")
     if _newer(FAKE_HOST_LIB, [src] + HEADERS):
@@ -116,6 +130,9 @@ def build_all(verbose=False):
     if os.path.exists(os.path.join(CSRC, "gpu_bfs_module.cpp")):
         build_bfs_module(objs, verbose)
     out = {"core": CORE_LIB}
+    if os.path.exists(os.path.join(CSRC, "katz_centrality_module.cpp")):
+        build_katz_module(objs, verbose)
+        out["katz_module"] = KATZ_MODULE_LIB
     if os.path.exists(os.path.join(CSRC, "gpu_bfs_module.cpp")):
         out["bfs_module"] = BFS_MODULE_LIB
     if os.path.exists(os.path.join(CSRC, "pagerank_module.cpp")):

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "core.hpp"
+#include "mgb200_katz.h"
 #include "rmat.hpp"
 
 struct mgb200_graph {
@@ -349,7 +350,7 @@ int mgb200_pagerank_run_partition(mgb200_graph *h, const mgb200_run_params *para
                                   uint32_t *vertex_out, mgb200_run_stats *stats_out) {
   if (!h || !params) return MGB200_ERR_INVALID_ARGUMENT;
   Graph &g = h->g;
-  if (g.part_world > 1 && !g.peers_connected) {
+  if (g.part_world > 1 && !g.peers_connected && !g.tun.lone_partition) {
     set_error("partition is not connected to its peers (mgb200_graph_connect_peers)");
     return MGB200_ERR_COMM;
   }
@@ -492,6 +493,55 @@ int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint6
   return MGB200_OK;
 }
 
+// ---- Katz centrality (include/mgb200_katz.h; kernels in katz.cu) -----------------------------------------
+
+int mgb200_katz_run(mgb200_graph *h, double alpha, double epsilon, uint64_t max_iterations, double *centrality_out,
+                    mgb200_katz_stats *stats_out) {
+  if (!h) return MGB200_ERR_INVALID_ARGUMENT;
+  Graph &g = h->g;
+  if (g.n > 0 && !centrality_out) {
+    set_error("centrality_out is null");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  MGB_CUDA(cudaSetDevice(g.device));
+  if (g.n > 0 && !g.out_stage) MGB_CUDA(cudaMalloc(&g.out_stage, g.n * sizeof(double)));  // kept for the handle's life
+  KatzResult res;
+  int rc = katz_iterate(g, alpha, epsilon, max_iterations, g.out_stage, &res);
+  if (rc) return rc;
+  if (g.n > 0) {
+    cudaError_t e = cudaMemcpyAsync(centrality_out, g.out_stage, g.n * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(centralities D2H)", __FILE__, __LINE__);
+  }
+  if (stats_out) {
+    stats_out->iterations = res.iterations;
+    stats_out->max_out_degree = res.max_out_degree;
+    stats_out->gamma = res.gamma;
+    stats_out->iterate_ms = res.iterate_ms;
+    stats_out->kernel_launches = res.launches;
+    stats_out->tie_order_runs = res.tie_order_runs;
+  }
+  if (!res.converged) {
+    set_error("Katz centrality: max_iterations reached before the ranking separated");
+    return MGB200_KATZ_NOT_CONVERGED;
+  }
+  return MGB200_OK;
+}
+
+int mgb200_katz_centrality(uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to, double alpha,
+                           double epsilon, uint64_t max_iterations, double *centrality_out, uint64_t *iterations_out) {
+  const char *dev_env = getenv("MGB200_DEVICE");
+  const int device = dev_env ? atoi(dev_env) : 0;
+  mgb200_graph *g = nullptr;
+  int rc = mgb200_graph_create_host(device, n, m, from, to, 0, 1, &g);  // fails without a device, also for n == 0
+  if (rc) return rc;
+  mgb200_katz_stats stats{};
+  rc = mgb200_katz_run(g, alpha, epsilon, max_iterations, centrality_out, &stats);
+  mgb200_graph_destroy(g);
+  if (iterations_out) *iterations_out = stats.iterations;
+  return rc;
+}
+
 int mgb200_partition_range(uint64_t n, uint32_t part_world, uint32_t part_rank, uint64_t *first_label_out,
                            uint64_t *rows_out) {
   if (part_world == 0 || part_world > static_cast<uint32_t>(kMaxPeers) || part_rank >= part_world) {
@@ -502,6 +552,56 @@ int mgb200_partition_range(uint64_t n, uint32_t part_world, uint32_t part_rank, 
   const uint64_t base = n / part_world, extra = n % part_world;
   if (first_label_out) *first_label_out = static_cast<uint64_t>(part_rank) * base + std::min<uint64_t>(part_rank, extra);
   if (rows_out) *rows_out = base + (part_rank < extra ? 1 : 0);
+  return MGB200_OK;
+}
+
+namespace {
+int make_row_map(uint64_t n, uint64_t heavy_rows, uint32_t part_world, int global_order, uint32_t part_rank,
+                 RowMap *map) {
+  if (part_world == 0 || part_world > static_cast<uint32_t>(kMaxPeers) || part_rank >= part_world ||
+      (global_order && heavy_rows > n)) {
+    set_error("invalid partition: rank " + std::to_string(part_rank) + " of " + std::to_string(part_world));
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  *map = RowMap{};
+  map->n = n;
+  map->heavy = global_order ? heavy_rows : 0;
+  map->world = part_world;
+  map->rank = part_rank;
+  map->global_order = global_order ? 1u : 0u;
+  map->finalize();
+  return MGB200_OK;
+}
+}  // namespace
+
+int mgb200_partition_locate(uint64_t n, uint64_t heavy_rows, uint32_t part_world, int global_order, uint64_t label,
+                            uint32_t *owner_out, uint64_t *local_row_out) {
+  RowMap map;
+  const int rc = make_row_map(n, heavy_rows, part_world, global_order, 0, &map);
+  if (rc != MGB200_OK) return rc;
+  if (label >= n) {
+    set_error("label out of range");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  if (owner_out) *owner_out = map.owner(label);
+  if (local_row_out) *local_row_out = map.local_of(label);
+  return MGB200_OK;
+}
+
+int mgb200_partition_label(uint64_t n, uint64_t heavy_rows, uint32_t part_world, int global_order, uint32_t part_rank,
+                           uint64_t local_row, uint64_t *label_out, uint64_t *rows_out) {
+  RowMap map;
+  const int rc = make_row_map(n, heavy_rows, part_world, global_order, part_rank, &map);
+  if (rc != MGB200_OK) return rc;
+  const uint64_t rows = map.local_rows(part_rank);
+  if (rows_out) *rows_out = rows;
+  if (label_out) {
+    if (local_row >= rows) {
+      set_error("local row out of range");
+      return MGB200_ERR_INVALID_ARGUMENT;
+    }
+    *label_out = map.label_of_local(local_row);
+  }
   return MGB200_OK;
 }
 

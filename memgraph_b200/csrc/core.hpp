@@ -31,6 +31,73 @@ constexpr uint32_t kIdxL1Hot = 0x40000000u;     // may allocate in L1, else bypa
 constexpr uint32_t kIdxLabelMask = 0x3FFFFFFFu; // the label itself: flagged graphs have n < 2^30
 constexpr uint32_t kNoL1Hints = 0xFFFFFFFFu;    // l1_hot_labels() when MGB200_L1_HOT_K < 0
 
+// Which labels a partition owns and how its local rows (ascending label) map onto them.
+//   dealt ranges (default): sorted position p -> owner p % P, label = start(owner) + p / P.  Every partition owns ONE
+//     contiguous label range whose prefix is its hot part ("hot" = P windows in label space).
+//   global order (MGB200_LABELLING=global): label = sorted position.  The `heavy` first labels (the heavy rows of the
+//     whole graph) are owned round-robin, label % P; after them, BLOCKS of 32 consecutive labels -- one SELL slice, one
+//     256-byte coalesced push per warp -- are owned round-robin.  "Hot" is one global label prefix on every partition,
+//     so the single-partition gather code (range policy, label < l1_hot) is exact everywhere, with no owner lookup.
+//     In-edge balance at P = 8: 1.0135 vs 1.0127 max/mean for the dealt ranges (profiles/r01_partition_balance.txt).
+#define MGB_HD __host__ __device__ __forceinline__
+struct RowMap {
+  uint64_t n = 0;
+  uint64_t heavy = 0;  // global order: number of heavy rows of the WHOLE graph (labels [0, heavy))
+  uint32_t world = 1, rank = 0;
+  uint32_t global_order = 0;
+  uint64_t row_lo = 0;   // dealt ranges: first label owned by `rank`             (set by finalize())
+  uint64_t heavy_q = 0;  // global order: heavy rows owned by `rank`               (set by finalize())
+
+  // ---- dealt ranges ----
+  MGB_HD uint64_t dealt_count(uint32_t q) const { return (n + world - 1 - q) / world; }
+  MGB_HD uint64_t dealt_start(uint32_t q) const {  // sum_{r<q} count(r): the first (n % world) owners hold one extra row
+    const uint64_t base = n / world, extra = n % world;
+    return static_cast<uint64_t>(q) * base + (q < extra ? q : extra);
+  }
+  // ---- global order ----
+  MGB_HD uint64_t heavy_rows(uint32_t q) const { return (heavy + world - 1 - q) / world; }  // labels q, q+P, .. < heavy
+  MGB_HD uint64_t blocks() const { return (n - heavy + kSliceRows - 1) / kSliceRows; }
+  // rows `q` owns in blocks [0, first_blocks) of the block sequence
+  MGB_HD uint64_t rows_in_blocks(uint32_t q, uint64_t first_blocks) const {
+    if (first_blocks == 0) return 0;
+    uint64_t rows = ((first_blocks + world - 1 - q) / world) * kSliceRows;
+    const uint64_t nb = blocks();
+    if (first_blocks == nb && (nb - 1) % world == q) rows -= nb * kSliceRows - (n - heavy);  // last block may be partial
+    return rows;
+  }
+  // ---- both ----
+  MGB_HD uint64_t local_rows(uint32_t q) const {
+    return global_order ? heavy_rows(q) + rows_in_blocks(q, blocks()) : dealt_count(q);
+  }
+  MGB_HD uint64_t label_of_pos(uint64_t pos) const {
+    return global_order ? pos : dealt_start(static_cast<uint32_t>(pos % world)) + pos / world;
+  }
+  MGB_HD uint32_t owner(uint64_t label) const {
+    if (global_order)
+      return static_cast<uint32_t>(label < heavy ? label % world : ((label - heavy) / kSliceRows) % world);
+    uint32_t q = 0;
+    for (uint32_t r = 1; r < world; ++r)
+      if (label >= dealt_start(r)) q = r;
+    return q;
+  }
+  MGB_HD uint64_t local_of(uint64_t label) const {  // local row of `label` on its owner
+    if (!global_order) return label - dealt_start(owner(label));
+    if (label < heavy) return label / world;
+    const uint64_t b = (label - heavy) / kSliceRows;
+    return heavy_rows(static_cast<uint32_t>(b % world)) + (b / world) * kSliceRows + (label - heavy) % kSliceRows;
+  }
+  MGB_HD uint64_t label_of_local(uint64_t r) const {  // local row of THIS partition -> label
+    if (!global_order) return row_lo + r;
+    if (r < heavy_q) return r * world + rank;
+    const uint64_t k = r - heavy_q;
+    return heavy + ((k / kSliceRows) * world + rank) * kSliceRows + k % kSliceRows;
+  }
+  void finalize() {
+    row_lo = (!global_order && n) ? dealt_start(rank) : 0;
+    heavy_q = global_order ? heavy_rows(rank) : 0;
+  }
+};
+
 // Written by iteration kernels, read by the host between batches (plain device memory).
 struct IterState {
   unsigned long long diff_bits;   // running max |delta| of the current iteration (bits of a double >= 0)
@@ -63,7 +130,8 @@ struct Graph {
   int sm_count = 0;
   uint64_t n = 0, m = 0;
   uint32_t part_rank = 0, part_world = 1;
-  uint64_t row_lo = 0;       // first global label owned
+  uint64_t row_lo = 0;       // first global label owned (dealt ranges; 0 under global-order labelling)
+  RowMap map;                // label <-> (owner, local row)
   uint64_t local_rows = 0;
   uint64_t local_edges = 0;
   uint64_t n_heavy = 0, n_sell = 0, n_zero = 0;
@@ -76,6 +144,8 @@ struct Graph {
   uint32_t *label_of = nullptr;     // [n]  original id -> global label
   uint32_t *outdeg_l = nullptr;     // [n]  out-degree by global label
   uint32_t *local_vertex = nullptr; // [local_rows] original id of each owned row
+  uint32_t *need_mask = nullptr;    // [ceil(local_rows / 4)] one BYTE per owned row: bit q = partition q gathers this
+                                    // row's contribution (has an in-edge from it); nullptr = push to every peer
 
   // heavy class
   uint64_t heavy_edges = 0;
@@ -121,19 +191,29 @@ struct Graph {
   cudaEvent_t join_ev = nullptr;
   bool overlap_epilogue = true;
   bool stream_attr_set = false;
+  // MGB200_PUSH=copy: the exchange as peer copies of this partition's contiguous label slices on the copy engines
+  // (one stream per peer), instead of NVLink stores issued by the epilogue kernels
+  cudaStream_t copy_streams[kMaxPeers] = {};
+  cudaEvent_t copy_done[kMaxPeers] = {};
+  cudaEvent_t sell_ready_ev = nullptr, heavy_ready_ev = nullptr;
   struct Tunables {  // environment, read once per graph in build_graph()
     uint64_t l2_hot_mb = 64;     // MGB200_L2_HOT_MB: evict-last window of the gathered vector (64 = effective L2, l2_bench)
     long l1_hot_k = 16;          // MGB200_L1_HOT_K: hottest labels (x1024) allowed to allocate in L1; <0 = no L1 hints
     bool multi_aware = true;     // MGB200_MULTI_AWARE=0: legacy "global label prefix is hot" on every partition
     bool force_multi_path = false;  // MGB200_FORCE_MULTI_PATH=1: run the multi-partition gather code on one GPU (measurement)
     bool stream_kernel = false;  // MGB200_SELL_KERNEL=stream
+    bool global_order = false;   // MGB200_LABELLING=global: label = global degree order, blocks of 32 dealt (RowMap)
+    bool push_mask = false;      // MGB200_PUSH_MASK=1: push a contribution only to the partitions that gather it
+    bool lone_partition = false; // MGB200_LONE_PARTITION=1 (profiling only): run ONE partition of part_world without its
+                                 // peers -- no stores to them, barrier of one; timings/ncu are real, ranks are NOT
+    bool push_copy = false;      // MGB200_PUSH=copy (dealt contiguous ranges only)
     int idx_flags = -1;          // MGB200_IDX_FLAGS: 1 bake hotness into the indices, 0 never, -1 (default) see build_graph
     int sell_chunks = 1;         // MGB200_SELL_CHUNKS
     unsigned long long barrier_timeout_ms = 20000;  // MGB200_BARRIER_TIMEOUT_MS
   } tun;
   // hot thresholds in LOCAL label units (label - first label of the owning partition); one definition for the
   // build-time index flags and the run-time gather window
-  uint32_t hot_divisor() const { return tun.multi_aware ? part_world : 1u; }
+  uint32_t hot_divisor() const { return (tun.multi_aware && !map.global_order) ? part_world : 1u; }
   uint32_t l1_hot_labels() const {
     if (tun.l1_hot_k < 0) return kNoL1Hints;
     const uint64_t v = static_cast<uint64_t>(tun.l1_hot_k) * 1024 / hot_divisor();
@@ -141,7 +221,7 @@ struct Graph {
   }
   uint32_t l2_hot_labels() const {
     if (!tun.multi_aware) return 0xFFFFFFFFu;
-    const uint64_t v = (tun.l2_hot_mb << 20) / sizeof(double) / part_world;
+    const uint64_t v = (tun.l2_hot_mb << 20) / sizeof(double) / hot_divisor();
     return static_cast<uint32_t>(v < 0xFFFFFFFFull ? v : 0xFFFFFFFFull);
   }
   // optional per-launch timing: an event pair around every kernel of the first kMaxTimedLaunches iterations
@@ -182,11 +262,21 @@ struct IterateConfig {
 constexpr int kSumBlocks = 1024;
 int launch_init(Graph &g, const IterateConfig &cfg);
 int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *launch_count, uint64_t *spmv_count);
+int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count);  // SELL sums + heavy partials only
 int launch_barrier(Graph &g);
 int launch_sum_and_exchange(Graph &g);
 int launch_write_ranks_original_order(Graph &g, double *d_out);                   // single partition
 int launch_write_ranks_local(Graph &g, double *d_rank_out, uint32_t *d_vertex_out);  // partitioned
 int kernel_occupancy_report(Graph &g, char *buf, size_t cap);
+
+// katz.cu
+struct KatzResult {
+  uint64_t iterations = 0, max_out_degree = 0, launches = 0, tie_order_runs = 0;
+  double gamma = 0.0, iterate_ms = 0.0;
+  bool converged = false;
+};
+int katz_iterate(Graph &g, double alpha, double epsilon, uint64_t max_iterations, double *d_out_original_order,
+                 KatzResult *res);
 
 // rmat.cu
 int rmat_device(int device, uint32_t scale, uint64_t first_edge, uint64_t count, uint64_t seed, double a, double b,

@@ -67,12 +67,12 @@ struct Dealer {  // sorted position -> global label when positions are dealt rou
   }
 };
 
-__global__ void label_kernel(Dealer deal, const uint32_t *sorted_id, const uint32_t *indeg, const uint32_t *outdeg,
+__global__ void label_kernel(RowMap map, const uint32_t *sorted_id, const uint32_t *indeg, const uint32_t *outdeg,
                              uint32_t *label_of, uint32_t *indeg_l, uint32_t *outdeg_l, uint32_t *vertex_of_label) {
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-  for (uint64_t pos = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; pos < deal.n; pos += stride) {
+  for (uint64_t pos = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; pos < map.n; pos += stride) {
     const uint32_t v = sorted_id[pos];
-    const uint64_t l = deal.label(pos);
+    const uint64_t l = map.label_of_pos(pos);
     label_of[v] = static_cast<uint32_t>(l);
     indeg_l[l] = indeg[v];
     outdeg_l[l] = outdeg[v];
@@ -90,7 +90,7 @@ __global__ void edge_key_all_kernel(uint64_t m, const uint32_t *from, const uint
 }
 
 __global__ void edge_key_owned_kernel(uint64_t m, const uint32_t *from, const uint32_t *to, const uint32_t *label_of,
-                                      uint64_t row_lo, uint64_t row_hi, uint64_t *key,
+                                      RowMap map, uint64_t row_hi, uint64_t *key,
                                       unsigned long long *cursor) {
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   const int lane = threadIdx.x & 31;
@@ -100,7 +100,7 @@ __global__ void edge_key_owned_kernel(uint64_t m, const uint32_t *from, const ui
     bool mine = false;
     if (e < m) {
       dl = label_of[to[e]];
-      mine = dl >= row_lo && dl < row_hi;
+      mine = map.global_order ? map.owner(dl) == map.rank : (dl >= map.row_lo && dl < row_hi);
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, mine);
     if (ballot == 0) continue;
@@ -109,7 +109,8 @@ __global__ void edge_key_owned_kernel(uint64_t m, const uint32_t *from, const ui
     base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
     if (mine) {
       const unsigned before = __popc(ballot & ((1u << lane) - 1u));
-      key[base + before] = ((dl - row_lo) << 32) | label_of[from[e]];
+      const uint64_t local = map.global_order ? map.local_of(dl) : dl - map.row_lo;
+      key[base + before] = (local << 32) | label_of[from[e]];
     }
   }
 }
@@ -148,6 +149,24 @@ __global__ void nonzero_per_partition_kernel(Dealer deal, const uint32_t *indeg_
       c += indeg_l[l] > 0;
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(nz + q, c);
+  }
+}
+
+// Which partitions gather the contribution of an owned row?  Every partition sees the whole edge list, so this is local
+// work: edge u -> v makes owner(v) a reader of u.  At P = 8 on RMAT only 48 % of the (vertex, peer) pairs are readers
+// (scripts/push_need.py): the other half of the NVLink pushes is never looked at.
+__global__ void need_mask_kernel(uint64_t m, const uint32_t *from, const uint32_t *to, const uint32_t *label_of,
+                                 RowMap map, uint32_t *words) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t e = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < m; e += stride) {
+    const uint64_t ul = label_of[from[e]];
+    if (map.owner(ul) != map.rank) continue;
+    const uint32_t q = map.owner(label_of[to[e]]);
+    if (q == map.rank) continue;
+    const uint64_t row = map.local_of(ul);
+    const uint32_t bit = (1u << q) << ((row & 3u) * 8u);
+    uint32_t *w = words + (row >> 2);
+    if ((*reinterpret_cast<volatile uint32_t *>(w) & bit) == 0) atomicOr(w, bit);  // hubs: one atomic, then reads
   }
 }
 
@@ -254,11 +273,11 @@ __global__ void sell_items_kernel(uint32_t n_items, uint64_t n_slices, const uin
   item_begin[i] = lo;
 }
 
-__global__ void gather_local_vertex_kernel(uint64_t rows, uint64_t row_lo, const uint32_t *vertex_of_label,
-                                           uint32_t *local_vertex) {
+// by_local[r] = by_label[label of this partition's local row r]  (original vertex ids, in-degrees)
+__global__ void gather_local_u32_kernel(uint64_t rows, RowMap map, const uint32_t *by_label, uint32_t *by_local) {
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   for (uint64_t r = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < rows; r += stride)
-    local_vertex[r] = vertex_of_label[row_lo + r];
+    by_local[r] = by_label[map.label_of_local(r)];
 }
 
 __global__ void narrow_kernel(uint64_t count, uint64_t n, const uint64_t *in, uint32_t *out, int *bad) {
@@ -335,6 +354,7 @@ void free_graph(Graph &g) {
   if (g.sell_item_begin) cudaFree(g.sell_item_begin);
   if (g.sell_sums) cudaFree(g.sell_sums);
   if (g.out_stage) cudaFree(g.out_stage);
+  if (g.need_mask) cudaFree(g.need_mask);
   void *ptrs[] = {g.label_of,  g.outdeg_l,  g.local_vertex, g.heavy_ptr,    g.heavy_idx, g.seg_row,     g.seg_begin,
                   g.seg_first, g.seg_partial, g.sell_colbase, g.sell_idx,     g.rank,      g.window,      g.state,
                   g.sum_partials};
@@ -348,6 +368,12 @@ void free_graph(Graph &g) {
   for (auto &e : g.fork_evs)
     if (e) cudaEventDestroy(e);
   if (g.join_ev) cudaEventDestroy(g.join_ev);
+  for (auto &e : g.copy_done)
+    if (e) cudaEventDestroy(e);
+  if (g.sell_ready_ev) cudaEventDestroy(g.sell_ready_ev);
+  if (g.heavy_ready_ev) cudaEventDestroy(g.heavy_ready_ev);
+  for (auto &cs : g.copy_streams)
+    if (cs) cudaStreamDestroy(cs);
   if (g.stream2) cudaStreamDestroy(g.stream2);
   if (g.stream) cudaStreamDestroy(g.stream);
 }
@@ -361,6 +387,8 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   MGB_CUDA(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
   for (auto &e : g.fork_evs) MGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   MGB_CUDA(cudaEventCreateWithFlags(&g.join_ev, cudaEventDisableTiming));
+  MGB_CUDA(cudaEventCreateWithFlags(&g.sell_ready_ev, cudaEventDisableTiming));
+  MGB_CUDA(cudaEventCreateWithFlags(&g.heavy_ready_ev, cudaEventDisableTiming));
   {
     const char *s = getenv("MGB200_OVERLAP_EPILOGUE");
     g.overlap_epilogue = !(s && s[0] == '0');
@@ -370,6 +398,10 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     if ((s = getenv("MGB200_FORCE_MULTI_PATH")) != nullptr) g.tun.force_multi_path = s[0] == '1';
     if ((s = getenv("MGB200_SELL_KERNEL")) != nullptr) g.tun.stream_kernel = strcmp(s, "stream") == 0;
     if ((s = getenv("MGB200_IDX_FLAGS")) != nullptr) g.tun.idx_flags = atoi(s);
+    if ((s = getenv("MGB200_LABELLING")) != nullptr) g.tun.global_order = strcmp(s, "global") == 0;
+    if ((s = getenv("MGB200_PUSH_MASK")) != nullptr) g.tun.push_mask = s[0] == '1';
+    if ((s = getenv("MGB200_LONE_PARTITION")) != nullptr) g.tun.lone_partition = s[0] == '1';
+    if ((s = getenv("MGB200_PUSH")) != nullptr) g.tun.push_copy = strcmp(s, "copy") == 0;
     if ((s = getenv("MGB200_SELL_CHUNKS")) != nullptr) g.tun.sell_chunks = std::max(1, atoi(s));
     if ((s = getenv("MGB200_BARRIER_TIMEOUT_MS")) != nullptr) {
       const unsigned long long ms = strtoull(s, nullptr, 10);
@@ -385,15 +417,20 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   MGB_CUDA(cudaEventRecord(g.ev[0], st));
   Scratch tmp;
   const Dealer deal{n, g.part_world};
+  RowMap &map = g.map;
+  map = RowMap{};
+  map.n = n;
+  map.world = g.part_world;
+  map.rank = g.part_rank;
+  map.global_order = (g.tun.global_order && g.part_world > 1) ? 1u : 0u;  // one partition: both labellings coincide
   // Hot flags in the stored indices replace the per-gather owner lookup on several partitions (default there);
   // on one partition the range policy already costs nothing per gather, so flags are opt-in (MGB200_IDX_FLAGS=1).
   // They need two index bits (n < 2^30) and partition-aware thresholds; the TMA stream kernel reads raw indices.
   g.idx_flagged = (g.tun.idx_flags > 0 || (g.tun.idx_flags < 0 && g.part_world > 1)) && g.tun.multi_aware &&
-                  !g.tun.stream_kernel && n < (1ull << 30);
+                  !g.tun.global_order && !g.tun.stream_kernel && n < (1ull << 30);
   const IndexFlags idx_flags{deal, g.l1_hot_labels(), g.l2_hot_labels(), g.idx_flagged ? 1u : 0u};
-  g.row_lo = n ? deal.start(g.part_rank) : 0;
-  g.local_rows = n ? deal.count(g.part_rank) : 0;
-  const uint64_t row_hi = g.row_lo + g.local_rows;
+  g.row_lo = 0;
+  g.local_rows = 0;  // known once the degrees are (global order: depends on the heavy-row count of the whole graph)
 
   // iteration state and exchange window exist even for an empty graph
   MGB_CUDA(keep_alloc(g, &g.state, 1));
@@ -412,12 +449,12 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   g.peers.contrib[0][g.part_rank] = g.contrib(0);
   g.peers.contrib[1][g.part_rank] = g.contrib(1);
   g.peers.flags[g.part_rank] = g.flags();
-  MGB_CUDA(keep_alloc(g, &g.rank, g.local_rows));
   MGB_CUDA(keep_alloc(g, &g.label_of, n));
   MGB_CUDA(keep_alloc(g, &g.outdeg_l, n));
-  MGB_CUDA(keep_alloc(g, &g.local_vertex, g.local_rows));
 
   if (n == 0) {
+    MGB_CUDA(keep_alloc(g, &g.rank, 0));
+    MGB_CUDA(keep_alloc(g, &g.local_vertex, 0));
     MGB_CUDA(cudaEventRecord(g.ev[1], st));
     MGB_CUDA(cudaStreamSynchronize(st));
     return MGB200_OK;
@@ -440,6 +477,27 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     set_error("edge endpoint out of range (>= number_of_nodes)");
     return MGB200_ERR_INVALID_ARGUMENT;
   }
+
+  // 1b. who owns what.  Global-order labelling deals the heavy rows singly and the rest in blocks of 32 labels, so it
+  // needs the heavy-row count (and, for the zero-row tail, the non-zero count) of the WHOLE graph first.
+  uint64_t nonzero_global = 0;
+  if (map.global_order) {
+    unsigned long long *gc = nullptr;
+    MGB_CUDA(tmp.alloc(&gc, 3));
+    MGB_CUDA(cudaMemsetAsync(gc, 0, 3 * sizeof(unsigned long long), st));
+    class_count_kernel<<<blocks_for(n, g.sm_count), kThreads, 0, st>>>(n, indeg, g.heavy_min_degree, gc);
+    unsigned long long gc_host[3] = {0, 0, 0};
+    MGB_CUDA(cudaMemcpyAsync(gc_host, gc, sizeof(gc_host), cudaMemcpyDeviceToHost, st));
+    MGB_CUDA(cudaStreamSynchronize(st));
+    map.heavy = gc_host[0];
+    nonzero_global = std::max<uint64_t>(gc_host[1], gc_host[0]);
+  }
+  map.finalize();
+  g.row_lo = map.row_lo;
+  g.local_rows = map.local_rows(g.part_rank);
+  const uint64_t row_hi = g.row_lo + g.local_rows;
+  MGB_CUDA(keep_alloc(g, &g.rank, g.local_rows));
+  MGB_CUDA(keep_alloc(g, &g.local_vertex, g.local_rows));
 
   // 2. global order: in-degree desc, out-degree desc, id asc (stable radix sort)
   uint64_t *vkey = nullptr, *vkey_alt = nullptr;
@@ -464,12 +522,24 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   uint32_t *indeg_l = nullptr, *vertex_of_label = nullptr;
   MGB_CUDA(tmp.alloc(&indeg_l, n));
   MGB_CUDA(tmp.alloc(&vertex_of_label, n));
-  label_kernel<<<blocks_for(n, g.sm_count), kThreads, 0, st>>>(deal, vid, indeg, outdeg, g.label_of, indeg_l,
+  label_kernel<<<blocks_for(n, g.sm_count), kThreads, 0, st>>>(map, vid, indeg, outdeg, g.label_of, indeg_l,
                                                               g.outdeg_l, vertex_of_label);
-  gather_local_vertex_kernel<<<blocks_for(g.local_rows, g.sm_count), kThreads, 0, st>>>(g.local_rows, g.row_lo,
-                                                                                       vertex_of_label,
-                                                                                       g.local_vertex);
-  const uint32_t *indeg_local = indeg_l + g.row_lo;
+  gather_local_u32_kernel<<<blocks_for(g.local_rows, g.sm_count), kThreads, 0, st>>>(g.local_rows, map, vertex_of_label,
+                                                                                    g.local_vertex);
+  const uint32_t *indeg_local = indeg_l + g.row_lo;  // dealt ranges: the owned labels are contiguous
+  if (map.global_order) {
+    uint32_t *gathered = nullptr;
+    MGB_CUDA(tmp.alloc(&gathered, g.local_rows));
+    gather_local_u32_kernel<<<blocks_for(g.local_rows, g.sm_count), kThreads, 0, st>>>(g.local_rows, map, indeg_l,
+                                                                                      gathered);
+    indeg_local = gathered;
+  }
+  if (g.tun.push_mask && g.part_world > 1 && m > 0 && g.local_rows > 0) {
+    const uint64_t words = (g.local_rows + 3) / 4;
+    MGB_CUDA(keep_alloc(g, &g.need_mask, words));
+    MGB_CUDA(cudaMemsetAsync(g.need_mask, 0, words * sizeof(uint32_t), st));
+    need_mask_kernel<<<blocks_for(m, g.sm_count), kThreads, 0, st>>>(m, d_from, d_to, g.label_of, map, g.need_mask);
+  }
 
   // 4. class boundaries and local edge count
   unsigned long long *counts = nullptr;
@@ -480,7 +550,20 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   unsigned long long counts_host[4] = {0, 0, 0, 0};
   MGB_CUDA(cudaMemcpyAsync(counts_host, counts, sizeof(counts_host), cudaMemcpyDeviceToHost, st));
   MGB_CUDA(cudaStreamSynchronize(st));
-  {
+  g.any_zero_rows = false;
+  uint64_t sell_rows_global_order = 0;
+  if (map.global_order) {
+    // Blocks [0, nz_blocks) hold at least one row with in-edges: they are SELL slices (the zero rows of the one mixed
+    // block are ordinary SELL rows of width 0).  Every label from zero_first on is a zero row on whichever partition
+    // owns it: ONE global tail range, the same on every partition.
+    const uint64_t nz_blocks = nonzero_global > map.heavy ? (nonzero_global - map.heavy + kSliceRows - 1) / kSliceRows : 0;
+    const uint64_t zero_first = std::min<uint64_t>(n, map.heavy + nz_blocks * kSliceRows);
+    sell_rows_global_order = map.rows_in_blocks(g.part_rank, nz_blocks);
+    for (uint32_t q = 0; q < g.part_world; ++q) g.part_start[q] = g.zero_lo[q] = g.zero_hi[q] = 0;
+    g.zero_lo[0] = zero_first;
+    g.zero_hi[0] = n;
+    g.any_zero_rows = zero_first < n;
+  } else {
     unsigned long long *nz = nullptr;
     MGB_CUDA(tmp.alloc(&nz, kMaxPeers));
     MGB_CUDA(cudaMemsetAsync(nz, 0, kMaxPeers * sizeof(unsigned long long), st));
@@ -488,7 +571,6 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     unsigned long long nz_host[kMaxPeers] = {};
     MGB_CUDA(cudaMemcpyAsync(nz_host, nz, sizeof(nz_host), cudaMemcpyDeviceToHost, st));
     MGB_CUDA(cudaStreamSynchronize(st));
-    g.any_zero_rows = false;
     for (uint32_t q = 0; q < g.part_world; ++q) {
       g.part_start[q] = deal.start(q);
       g.zero_lo[q] = deal.start(q) + nz_host[q];
@@ -497,8 +579,12 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     }
   }
   g.n_heavy = counts_host[0];
-  g.n_sell = counts_host[1] - counts_host[0];
-  g.n_zero = g.local_rows - counts_host[1];
+  if (map.global_order && g.n_heavy != map.heavy_q) {
+    set_error("internal: heavy rows owned (" + std::to_string(g.n_heavy) + ") != dealt (" + std::to_string(map.heavy_q) + ")");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  g.n_sell = map.global_order ? sell_rows_global_order : counts_host[1] - counts_host[0];
+  g.n_zero = g.local_rows - g.n_heavy - g.n_sell;
   g.local_edges = counts_host[2];
 
   // 5. keys of the owned edges, sorted by (local row, source label)
@@ -510,8 +596,8 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
       edge_key_all_kernel<<<blocks_for(m, g.sm_count), kThreads, 0, st>>>(m, d_from, d_to, g.label_of, ekey);
     } else {
       MGB_CUDA(cudaMemsetAsync(counts + 3, 0, sizeof(unsigned long long), st));
-      edge_key_owned_kernel<<<blocks_for(m, g.sm_count), kThreads, 0, st>>>(m, d_from, d_to, g.label_of, g.row_lo,
-                                                                           row_hi, ekey, counts + 3);
+      edge_key_owned_kernel<<<blocks_for(m, g.sm_count), kThreads, 0, st>>>(m, d_from, d_to, g.label_of, map, row_hi,
+                                                                           ekey, counts + 3);
     }
   }
   if (g.local_edges) {

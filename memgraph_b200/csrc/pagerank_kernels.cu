@@ -188,9 +188,12 @@ struct RowEpilogue {
   double damping;  // d
   double *rank;            // [local_rows]
   const uint32_t *outdeg;  // [n] by global label
-  uint64_t row_lo;
+  RowMap map;              // local row -> global label
   double *contrib_out[kMaxPeers];  // this iteration's output buffer on every partition (self included)
   int world;
+  int self;                // this partition
+  const uint8_t *need;     // [local_rows] bit q: partition q gathers this row's contribution; nullptr = everyone
+  uint32_t store_mask;     // bit q: the epilogue stores into partition q's buffer (all ones; self only under MGB200_PUSH=copy)
 };
 
 // rank_next = base + d * acc as two separately rounded operations, like the reference's
@@ -200,16 +203,19 @@ __device__ __forceinline__ double finish_row(const RowEpilogue &ep, uint64_t loc
   const double next = __dadd_rn(ep.base, __dmul_rn(ep.damping, acc));
   const double prev = ld_stream_f64(ep.rank + local_row, stream_pol);
   st_stream_f64(ep.rank + local_row, next, stream_pol);
-  const uint64_t label = ep.row_lo + local_row;
+  const uint64_t label = ep.map.label_of_local(local_row);
   const uint32_t od = ld_index(ep.outdeg + label, stream_pol);
   // A vertex without out-edges is never a gather source, so its contribution is never read: no division,
   // no store, and -- what matters across GPUs -- no NVLink push.  Labels are sorted by (in-degree, out-degree)
   // descending, so these vertices are the contiguous tail of every in-degree class: whole warps skip.
   if (od != 0) {
     const double c = __ddiv_rn(next, static_cast<double>(od));  // :93 quotient, once per vertex
+    // push only to the partitions that have an in-edge from this vertex (graph_build.cu need_mask_kernel)
+    const uint32_t need = ep.need ? (static_cast<uint32_t>(ep.need[local_row]) | (1u << ep.self)) : 0xFFu;
 #pragma unroll
     for (int q = 0; q < kMaxPeers; ++q) {
-      if (q < ep.world) st_stream_f64(ep.contrib_out[q] + label, c, stream_pol);  // q != self: NVLink store
+      if (q < ep.world && (((need & ep.store_mask) >> q) & 1u))
+        st_stream_f64(ep.contrib_out[q] + label, c, stream_pol);  // q != self: NVLink store
     }
   }
   return fabs(next - prev);
@@ -677,8 +683,13 @@ RowEpilogue make_epilogue(const Graph &g, uint64_t it, const IterateConfig &cfg)
   ep.damping = cfg.damping;
   ep.rank = g.rank;
   ep.outdeg = g.outdeg_l;
-  ep.row_lo = g.row_lo;
+  ep.map = g.map;
   ep.world = static_cast<int>(g.part_world);
+  ep.self = static_cast<int>(g.part_rank);
+  ep.need = reinterpret_cast<const uint8_t *>(g.need_mask);
+  ep.store_mask = ((g.tun.push_copy && g.part_world > 1 && !g.map.global_order) || g.tun.lone_partition)
+                      ? (1u << g.part_rank)
+                      : 0xFFFFFFFFu;
   const int out_parity = static_cast<int>((it + 1) & 1ull);
   for (int q = 0; q < kMaxPeers; ++q) ep.contrib_out[q] = q < ep.world ? g.peers.contrib[out_parity][q] : nullptr;
   return ep;
@@ -695,9 +706,10 @@ GatherWindow make_window(const Graph &g) {
   w.world = g.part_world;
   w.l1_hot = g.l1_hot_labels();
   w.l2_hot = g.l2_hot_labels();
+  // global-order labelling: "hot" is one label prefix on every partition -> the exact single-partition code
   w.path = g.idx_flagged ? kPathFlags
-           : (g.tun.multi_aware && (g.part_world > 1 || g.tun.force_multi_path)) ? kPathLookup
-                                                                                 : kPathRange;
+           : (g.tun.multi_aware && !g.map.global_order && (g.part_world > 1 || g.tun.force_multi_path)) ? kPathLookup
+                                                                                                        : kPathRange;
   for (uint32_t q = 0; q < static_cast<uint32_t>(kMaxPeers); ++q)
     w.start[q] = q < g.part_world ? static_cast<uint32_t>(g.part_start[q]) : 0xFFFFFFFFu;
   return w;
@@ -710,6 +722,11 @@ BarrierArgs make_barrier(const Graph &g) {
   b.rank = static_cast<int>(g.part_rank);
   b.world = static_cast<int>(g.part_world);
   for (int q = 0; q < kMaxPeers; ++q) b.peer[q] = q < b.world ? g.peers.flags[q] : nullptr;
+  if (g.tun.lone_partition) {  // profiling: a barrier of one over the own flag page
+    b.rank = 0;
+    b.world = 1;
+    for (int q = 0; q < kMaxPeers; ++q) b.peer[q] = q == 0 ? g.flags() : nullptr;
+  }
   b.timeout_ns = g.tun.barrier_timeout_ms * 1000000ull;
   return b;
 }
@@ -748,6 +765,36 @@ int launch_barrier(Graph &g) {
   return MGB200_OK;
 }
 
+// MGB200_PUSH=copy: ship labels [first_label, first_label + count) of this partition's freshly written contribution
+// buffer to every peer with one peer copy each, on per-peer streams (copy engines; no SM is involved and the NVLink
+// traffic no longer shares the SMs' store path with the heavy-row gathers).  `ready` orders the copies after the kernel
+// that produced the slice; finish_peer_copies() makes the main stream wait for all of them.
+int enqueue_peer_copies(Graph &g, int parity, uint64_t first_label, uint64_t count, cudaEvent_t ready,
+                        bool used[kMaxPeers]) {
+  if (count == 0) return MGB200_OK;
+  for (uint32_t q = 0; q < g.part_world; ++q) {
+    if (q == g.part_rank) continue;
+    if (!g.copy_streams[q]) {
+      MGB_CUDA(cudaStreamCreateWithFlags(&g.copy_streams[q], cudaStreamNonBlocking));
+      MGB_CUDA(cudaEventCreateWithFlags(&g.copy_done[q], cudaEventDisableTiming));
+    }
+    MGB_CUDA(cudaStreamWaitEvent(g.copy_streams[q], ready, 0));
+    MGB_CUDA(cudaMemcpyAsync(g.peers.contrib[parity][q] + first_label, g.contrib(parity) + first_label,
+                             count * sizeof(double), cudaMemcpyDefault, g.copy_streams[q]));
+    used[q] = true;
+  }
+  return MGB200_OK;
+}
+
+int finish_peer_copies(Graph &g, const bool used[kMaxPeers]) {
+  for (uint32_t q = 0; q < g.part_world; ++q) {
+    if (!used[q]) continue;
+    MGB_CUDA(cudaEventRecord(g.copy_done[q], g.copy_streams[q]));
+    MGB_CUDA(cudaStreamWaitEvent(g.stream, g.copy_done[q], 0));
+  }
+  return MGB200_OK;
+}
+
 // One iteration.  Main stream: (iteration 1: zero-row contribution refresh) -> SELL rows -> heavy segments ->
 // heavy finish -> [join] -> iteration end.  Side stream: the SELL epilogue, forked after the SELL rows:
 // it is the kernel that pushes contributions to the peer GPUs (NVLink-bound), so it overlaps with the
@@ -758,6 +805,9 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
   const RowEpilogue ep = make_epilogue(g, it, cfg);
   const double *contrib_in = g.contrib(static_cast<int>(it & 1ull));
   uint64_t launches = 0;
+  const bool push_copy = g.tun.push_copy && g.part_world > 1 && !g.map.global_order && !g.tun.lone_partition;  // needs contiguous label ranges
+  const int out_parity = static_cast<int>((it + 1) & 1ull);
+  bool copy_used[kMaxPeers] = {};
   const bool timed = g.time_spmv && g.timed_launches < Graph::kMaxTimedLaunches;
   auto tick = [&](int cls, int edge, cudaStream_t st) -> cudaError_t {
     if (!timed) return cudaSuccess;
@@ -850,6 +900,11 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
       if (c == chunks - 1) MGB_CUDA(tick(Graph::kClsSellEpi, 1, es));
     }
     if (stream_kernel) ++launches;
+    if (push_copy && g.n_sell > 0) {  // the SELL rows' slice is final once the epilogue kernel has run
+      MGB_CUDA(cudaEventRecord(g.sell_ready_ev, es));
+      const int crc = enqueue_peer_copies(g, out_parity, g.row_lo + g.n_heavy, g.n_sell, g.sell_ready_ev, copy_used);
+      if (crc) return crc;
+    }
     if (forked) MGB_CUDA(cudaEventRecord(g.join_ev, g.stream2));
     if (spmv_count) *spmv_count += 1;
   }
@@ -883,8 +938,17 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     heavy_finish_kernel<<<grid, kBlockThreads, 0, g.stream>>>(h);
     MGB_CUDA(tick(Graph::kClsHeavyFin, 1, g.stream));
     launches += 2;
+    if (push_copy && g.n_heavy > 0) {
+      MGB_CUDA(cudaEventRecord(g.heavy_ready_ev, g.stream));
+      const int crc = enqueue_peer_copies(g, out_parity, g.row_lo, g.n_heavy, g.heavy_ready_ev, copy_used);
+      if (crc) return crc;
+    }
   }
   if (forked) MGB_CUDA(cudaStreamWaitEvent(g.stream, g.join_ev, 0));
+  if (push_copy) {
+    const int crc = finish_peer_copies(g, copy_used);
+    if (crc) return crc;
+  }
   IterEndArgs e{};
   e.bar = make_barrier(g);
   e.max_iterations = cfg.max_iterations;
@@ -900,6 +964,60 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
   ++launches;
   MGB_CUDA(cudaGetLastError());
   if (timed) ++g.timed_launches;
+  if (launch_count) *launch_count += launches;
+  return MGB200_OK;
+}
+
+// The gather phase alone, over an arbitrary per-label vector vec_in[n + 1] (slot n must hold 0): SELL row sums into
+// g.sell_sums, heavy segment partials into g.seg_partial (summed per row by the caller in segment order).  This is
+// y = A^T x for the rows of this partition with PageRank's kernels and cache policies; other SpMV-shaped paths hang
+// their own epilogue on it (Katz: omega_i = A^T omega_{i-1}, katz.cu).  Kernels return at once while state->done is set.
+int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count) {
+  uint64_t launches = 0;
+  const GatherWindow window = make_window(g);
+  if (g.n_slices > 0) {
+    SellArgs s{};
+    s.colbase = g.sell_colbase;
+    s.idx = g.sell_idx;
+    s.slice_begin = 0;
+    s.n_slices = g.n_slices;
+    s.first_row = g.n_heavy;
+    s.end_row = g.n_heavy + g.n_sell;
+    s.contrib_in = vec_in;
+    s.window = window;
+    s.state = g.state;
+    s.sums = g.sell_sums;
+    void (*const sell_fn)(SellArgs) = window.path == kPathFlags    ? sell_rows_kernel<kPathFlags>
+                                      : window.path == kPathLookup ? sell_rows_kernel<kPathLookup>
+                                                                   : sell_rows_kernel<kPathRange>;
+    const int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_fn))),
+                                               ceil_div(g.n_slices, kWarpsPerBlock)));
+    sell_fn<<<grid, kBlockThreads, 0, g.stream>>>(s);
+    ++launches;
+  }
+  if (g.n_seg > 0) {
+    HeavyArgs h{};
+    h.heavy_ptr = g.heavy_ptr;
+    h.heavy_idx = g.heavy_idx;
+    h.seg_row = g.seg_row;
+    h.seg_begin = g.seg_begin;
+    h.seg_first = g.seg_first;
+    h.seg_partial = g.seg_partial;
+    h.n_seg = g.n_seg;
+    h.n_heavy = g.n_heavy;
+    h.segment_edges = g.segment_edges;
+    h.contrib_in = vec_in;
+    h.window = window;
+    h.state = g.state;
+    void (*const heavy_fn)(HeavyArgs) = window.path == kPathFlags    ? heavy_segments_kernel<kPathFlags>
+                                        : window.path == kPathLookup ? heavy_segments_kernel<kPathLookup>
+                                                                     : heavy_segments_kernel<kPathRange>;
+    const int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_fn))),
+                                               ceil_div(g.n_seg, kWarpsPerBlock)));
+    heavy_fn<<<grid, kBlockThreads, 0, g.stream>>>(h);
+    ++launches;
+  }
+  MGB_CUDA(cudaGetLastError());
   if (launch_count) *launch_count += launches;
   return MGB200_OK;
 }

@@ -75,3 +75,16 @@ extern "C" int oracle_katz(uint64_t n, uint64_t m, const uint64_t *from, const u
   if (iterations_out) *iterations_out = iteration;
   return converged ? 0 : 3;
 }
+
+// The order std::partial_sort(begin, end, end, comp) leaves n (id, key) pairs in, ids ascending on entry -- the exact
+// call of Converged (:185-189).  Checker for the product's index-arithmetic restatement of that permutation
+// (memgraph_b200/csrc/katz_heap.hpp, tests/test_katz_tie_order.py).
+extern "C" int oracle_partial_sort_order(uint64_t n, const double *keys, uint32_t *order_out) {
+  std::vector<std::pair<uint64_t, double>> active;
+  active.reserve(n);
+  for (uint64_t v = 0; v < n; ++v) active.emplace_back(v, keys[v]);
+  std::partial_sort(active.begin(), active.end(), active.end(),
+                    [](std::pair<uint64_t, double> a, std::pair<uint64_t, double> b) -> bool { return a.second > b.second; });
+  for (uint64_t i = 0; i < n; ++i) order_out[i] = static_cast<uint32_t>(active[i].first);
+  return 0;
+}

@@ -18,6 +18,16 @@ def build_checkers():
     subprocess.run(["make", "-s", "-C", os.path.join(REPO, "oracle"), "all"], check=True)
 
 
+def ensure_checkers_fresh():
+    """Rebuild the plain-C/C++ restatements when a source under oracle/ is newer than the library.  Called once at
+    session start (conftest.py), BEFORE anything dlopen()s the library: a stale copy that is already loaded stays
+    loaded, so rebuilding later in the session cannot add a missing symbol."""
+    import glob
+    srcs = glob.glob(os.path.join(REPO, "oracle", "*.c")) + glob.glob(os.path.join(REPO, "oracle", "*.cpp"))
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(f) for f in srcs):
+        subprocess.run(["make", "-s", "-C", os.path.join(REPO, "oracle"), "oracle"], check=True)
+
+
 class OracleError(RuntimeError):
     pass
 

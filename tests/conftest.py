@@ -15,6 +15,9 @@ if REPO not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _checkers import ensure_checkers_fresh
+    ensure_checkers_fresh()
 
 
 def _have_gpu():

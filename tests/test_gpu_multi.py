@@ -46,10 +46,16 @@ def run_partitioned(mg, n, f, t, world, **kw):
     return out, results, infos
 
 
+@pytest.mark.parametrize("labelling,push_mask,push", [("dealt", "0", "store"), ("global", "0", "store"),
+                                                       ("dealt", "1", "store"), ("global", "1", "store"),
+                                                       ("dealt", "0", "copy")])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_partitioned_equals_oracle(world):
+def test_partitioned_equals_oracle(world, labelling, push_mask, push, monkeypatch):
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    monkeypatch.setenv("MGB200_LABELLING", labelling)  # csrc/core.hpp RowMap: contiguous dealt ranges / global order
+    monkeypatch.setenv("MGB200_PUSH_MASK", push_mask)  # 1: contributions go only to the partitions that gather them
+    monkeypatch.setenv("MGB200_PUSH", push)            # copy: the exchange as peer copies on the copy engines
     import memgraph_b200 as mg
     oracle = Oracle()
     scale = 16
@@ -64,6 +70,7 @@ def test_partitioned_equals_oracle(world):
         assert sum(i["local_rows"] for i in infos) == n and sum(i["local_edges"] for i in infos) == m
         edges = [i["local_edges"] for i in infos]
         assert max(edges) < 1.25 * (m / world) + 70000  # dealt round-robin by degree rank: edge-balanced
+        assert all(i["heavy_rows"] + i["sell_rows"] + i["zero_rows"] == i["local_rows"] for i in infos)
 
 
 def test_partitioned_matches_single_gpu_bitwise_sum():
