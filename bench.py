@@ -120,44 +120,62 @@ def ncu_traffic():
 
 # ---- reference arm / cpu baseline -------------------------------------------------------------------------
 
-def cpu_reference_run(scale, steps, warmup, threads=None, single_thread_too=False):
-    """Times the reference's ParallelIterativePageRank (only that call, like the GPU side) on an RMAT
-    graph of `scale`.  Returns dict(value, kind, cores, sample, ms_per_step, build_s)."""
+REF_THREAD_CANDIDATES = (1, 2, 4, 8, 16, 32, 64)
+
+
+def _ref_impl():
+    """(impl, kind): the reference's own pagerank.cpp compiled in place (oracle/_ref) or, where that is absent,
+    the plain-C port.  Neither imports the product package: the RMAT input comes from oracle/rmat_oracle.c."""
     sys.path.insert(0, os.path.join(REPO, "tests"))
     from _checkers import Oracle, Reference  # noqa: E402  (bench.py's reference leg may execute oracle/)
-    import memgraph_b200 as mg
-    threads = threads or os.cpu_count() or 1
-    n, m = 1 << scale, EDGE_FACTOR << scale
-    s, t = mg.rmat_edges_host(scale, m, seed=SEED)
-    t0 = time.perf_counter()
     if Reference.available():
-        impl, kind = Reference(), "reference"
-        g = impl.graph(n, s, t)
-        run = lambda: impl.run(g, n, max_iterations=ITERATIONS, damping_factor=DAMPING, stop_epsilon=0.0,
-                               num_of_threads=threads)
-    else:
-        impl, kind = Oracle(), "port"
-        g = impl.graph(n, s, t)
-        threads = 1  # the C port walks the blocks sequentially
-        run = lambda: impl.run(g, n, max_iterations=ITERATIONS, damping_factor=DAMPING, stop_epsilon=0.0,
-                               num_of_threads=1)
-    build_s = time.perf_counter() - t0
-    for _ in range(warmup):
-        run()
+        return Reference(), "reference"
+    return Oracle(), "port"
+
+
+def cpu_reference_run(scale, steps, warmup, threads=None, sweep=True):
+    """Times the reference's ParallelIterativePageRank (only that call, like the GPU side) on the benchmark's RMAT
+    graph of `scale`.  The reference's thread count is a tunable with an interior optimum (every iteration merges one
+    full-length vector per thread on the main thread, pagerank.cpp:104-112, so more threads eventually lose): with
+    `sweep` one call per candidate T is timed first and the timed steps run at the best T.  Returns a dict."""
+    impl, kind = _ref_impl()
+    from _checkers import oracle_rmat_edges  # noqa: E402
+    hw = os.cpu_count() or 1
+    n, m = 1 << scale, EDGE_FACTOR << scale
+    s, t = oracle_rmat_edges(scale, m, seed=SEED)
     t0 = time.perf_counter()
-    for _ in range(steps):
-        run()
-    dt = time.perf_counter() - t0
-    one_thread = None
-    if kind == "reference" and threads > 1 and single_thread_too:
+    g = impl.graph(n, s, t)
+    build_s = time.perf_counter() - t0
+    del s, t
+
+    def call(T):
         t1 = time.perf_counter()
-        impl.run(g, n, max_iterations=ITERATIONS, damping_factor=DAMPING, stop_epsilon=0.0, num_of_threads=1)
-        one_thread = m * ITERATIONS / (time.perf_counter() - t1)
+        impl.run(g, n, max_iterations=ITERATIONS, damping_factor=DAMPING, stop_epsilon=0.0, num_of_threads=T)
+        return time.perf_counter() - t1
+
+    sweep_s = {}
+    if kind != "reference":
+        threads = 1  # the C port walks the thread blocks sequentially
+    elif threads is None:
+        cands = sorted({c for c in REF_THREAD_CANDIDATES if c <= hw} | {hw}) if sweep else [min(8, hw)]
+        for T in cands:
+            sweep_s[T] = call(T)
+            if T > 1 and sweep_s[T] > 2.5 * min(sweep_s.values()):
+                break  # past the optimum and getting worse: larger T only adds serial merge work
+        threads = min(sweep_s, key=sweep_s.get)
+    for _ in range(warmup):
+        call(threads)
+    times = [call(threads) for _ in range(steps)]
+    dt = float(sum(times))
     impl.free(g)
+    eps = lambda sec: m * ITERATIONS / sec
     return {"value": m * ITERATIONS * steps / dt, "unit": "edges/s", "cores": threads, "kind": kind,
-            "value_1_thread": one_thread,
+            "threads": threads, "host_threads_available": hw, "scale": scale, "best_of": len(sweep_s) or 1,
+            "thread_sweep_edges_per_s": {str(k): eps(v) for k, v in sweep_s.items()},
+            "value_1_thread": eps(sweep_s[1]) if 1 in sweep_s else None,
             "sample": f"RMAT scale-{scale} EF{EDGE_FACTOR} (N={n}, E={m}), {ITERATIONS} iterations, stop_epsilon=0, "
-                      f"{steps} timed call(s) of ParallelIterativePageRank; graph ctor {build_s:.1f}s excluded",
+                      f"{steps} timed call(s) of ParallelIterativePageRank at its best thread count T={threads} "
+                      f"(swept {sorted(sweep_s)} of {hw} host threads); graph ctor {build_s:.1f}s excluded",
             "ms_per_step": dt / steps * 1e3, "build_s": build_s}
 
 
@@ -165,28 +183,34 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    # Bounded sample: the reference's cost per call grows like threads x N (every iteration merges one full-length
-    # vector per thread on the main thread) -- 36 s per call at scale-22 on a 128-thread host.  Calibrate on a
-    # small graph, then take the largest scale <= --cpu-scale that keeps (steps + warmup) calls within ~150 s.
+    # Bounded sample.  Same generator, same parameters, same call as the B200 arm; only the RMAT scale is bounded so
+    # that ctor + thread sweep + (steps + warmup) calls stay within MGB200_REF_BUDGET_S (default 240 s).  Cost model
+    # from a scale-20 probe at its best T: the call and the ctor grow ~2.4x per scale once the rank vectors leave the caches.
+    budget = float(os.environ.get("MGB200_REF_BUDGET_S", "240"))
     calls = max(1, args.steps) + max(0, args.warmup)
-    probe_scale = min(18, args.cpu_scale)
+    cap = min(args.cpu_scale, args.scale)
+    probe_scale = min(20, cap)
     probe = cpu_reference_run(probe_scale, 1, 0)
-    per_call_s = probe["ms_per_step"] / 1e3
+    per_call, ctor = probe["ms_per_step"] / 1e3, probe["build_s"]
     scale = probe_scale
-    while scale < args.cpu_scale and per_call_s * 2 * calls <= 150.0:
+    est = lambda pc, ct: ct + pc * (calls + 6)  # 6 ~ the thread sweep
+    while scale < cap and est(per_call * 2.4, ctor * 2.4) <= budget:
         scale += 1
-        per_call_s *= 2
-    log(f"reference arm: probe scale-{probe_scale} {probe['ms_per_step']:.0f} ms/call -> sample scale-{scale} "
-        f"(~{per_call_s:.1f} s/call x {calls} calls)")
-    res = probe if (scale == probe_scale and calls == 1) else cpu_reference_run(scale, max(1, args.steps), max(0, args.warmup))
-    args.cpu_scale = scale
+        per_call *= 2.4
+        ctor *= 2.4
+    log(f"reference arm: probe scale-{probe_scale} {probe['ms_per_step']:.0f} ms/call at T={probe['threads']} -> "
+        f"sample scale-{scale} (~{per_call:.1f} s/call x {calls} calls + ctor ~{ctor:.0f} s, budget {budget:.0f} s)")
+    res = cpu_reference_run(scale, max(1, args.steps), max(0, args.warmup))
     line = {
         "impl": "reference", "metric": "pagerank_edges_per_second", "value": res["value"], "unit": "edges/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"PageRank RMAT scale-{args.scale} EF16, 20 iterations, d=0.85, stop_epsilon=0 "
-                               f"(reference arm: bounded sample = RMAT scale-{args.cpu_scale})"},
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"PageRank RMAT scale-{args.scale} EF16, {ITERATIONS} iterations, d={DAMPING}, "
+                               f"stop_epsilon=0, seed {SEED} (reference arm: bounded sample = the same generator at "
+                               f"RMAT scale-{scale}, capped by --cpu-scale {args.cpu_scale} and a {budget:.0f} s budget)",
+                   "sample_scale": scale, "threads": res["threads"]},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "threads", "scale", "best_of",
+                                             "host_threads_available", "value_1_thread", "thread_sweep_edges_per_s")},
         "e2e": {"value": res["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -407,8 +431,9 @@ def run_b200_arm(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = cpu_reference_run(args.cpu_scale, 1, 0, single_thread_too=True)
-            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "value_1_thread")}
+            r = cpu_reference_run(min(args.cpu_scale, 22), 1, 0)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "threads", "scale", "best_of",
+                                     "host_threads_available", "value_1_thread", "thread_sweep_edges_per_s")}
         except Exception as ex:
             log("cpu_baseline failed:", ex)
 
@@ -481,7 +506,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=int, default=int(os.environ.get("MGB200_BENCH_SCALE", "26")))
-    ap.add_argument("--cpu-scale", type=int, default=int(os.environ.get("MGB200_CPU_SCALE", "22")),
+    ap.add_argument("--cpu-scale", type=int, default=int(os.environ.get("MGB200_CPU_SCALE", "24")),
                     help="RMAT scale of the bounded CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="pagerank", choices=["pagerank", "bfs"],

@@ -32,6 +32,23 @@ class OracleError(RuntimeError):
     pass
 
 
+def oracle_rmat_edges(scale, count=None, seed=42, a=0.57, b=0.19, c=0.19, first=0, threads=None):
+    """oracle/rmat_oracle.c: the benchmark's RMAT edge stream as uint64 (from, to) WITHOUT the product library."""
+    if not os.path.exists(ORACLE_SO):
+        build_checkers()
+    L = ctypes.CDLL(ORACLE_SO)
+    L.oracle_rmat_edges.argtypes = [ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_double,
+                                    ctypes.c_double, ctypes.c_double, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
+    count = (16 << scale) if count is None else count
+    frm = np.empty(count, dtype=np.uint64)
+    to = np.empty(count, dtype=np.uint64)
+    rc = L.oracle_rmat_edges(scale, first, count, seed, a, b, c, threads or min(os.cpu_count() or 1, 32),
+                             frm.ctypes.data, to.ctypes.data)
+    if rc:
+        raise OracleError(f"oracle_rmat_edges failed: {rc}")
+    return frm, to
+
+
 def _u64(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
 

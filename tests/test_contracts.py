@@ -63,6 +63,27 @@ def test_reference_arm_prints_one_contract_line():
     assert "workload" in d["config"] and "model" not in d["config"]
 
 
+def test_reference_arm_never_maps_the_product_library():
+    """The reference arm holds only oracle/ code: its RMAT input comes from oracle/rmat_oracle.c, not from the package."""
+    code = ("import sys, os; sys.argv=['bench.py','--impl','reference','--cpu-scale','12','--steps','1','--warmup','0'];"
+            "import runpy\n"
+            "try:\n    runpy.run_path('bench.py', run_name='__main__')\nexcept SystemExit: pass\n"
+            "maps=open('/proc/self/maps').read(); bad=[l for l in maps.splitlines() if 'memgraph_b200/_build' in l];"
+            "sys.stderr.write('MAPPED_PRODUCT=%d\\n' % len(bad)); assert 'memgraph_b200' not in sys.modules")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=REPO)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "MAPPED_PRODUCT=0" in r.stderr, r.stderr[-500:]
+
+
+def test_reference_arm_reports_its_thread_sweep():
+    r = run_bench("--impl", "reference", "--cpu-scale", "13", "--steps", "1", "--warmup", "0")
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    cb = d["cpu_baseline"]
+    assert cb["scale"] == 13 and cb["threads"] == cb["cores"] and cb["best_of"] >= 1
+    if cb["kind"] == "reference":
+        assert "1" in cb["thread_sweep_edges_per_s"] and cb["value_1_thread"] > 0
+
+
 def test_reference_arm_is_rank0_only_under_torchrun():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "2"],
