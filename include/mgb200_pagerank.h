@@ -134,6 +134,13 @@ int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint6
                                              uint32_t number_of_threads, uint32_t gpu_count, const int *devices,
                                              double *rank_out, uint64_t *iterations_out);
 
+/* The same with a parameter block, so that the cooperative-abort hook works across GPUs too: should_abort is polled
+ * from the CALLING thread only (Memgraph's mgp_must_abort must not be called from other threads, mg_procedure.h:75-81)
+ * and the first request becomes a collective stop on all partitions -> MGB200_ERR_ABORTED.  rank_out is host memory. */
+int mgb200_pagerank_multi(uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
+                          const mgb200_run_params *params, uint32_t number_of_threads, uint32_t gpu_count,
+                          const int *devices, double *rank_out, uint64_t *iterations_out);
+
 /* ---- multi-GPU: one partition per GPU, contributions pushed to peers over NVLink --------------- */
 
 #define MGB200_IPC_HANDLE_BYTES 64

@@ -56,6 +56,7 @@ EXPORTS = {
     "mgb200_parallel_iterative_pagerank": (i32, [u64, u64, vp, vp, u64, f64, f64, u32, vp, ctypes.POINTER(u64)]),
     "mgb200_parallel_iterative_pagerank_multi": (i32, [u64, u64, vp, vp, u64, f64, f64, u32, u32, vp, vp,
                                                        ctypes.POINTER(u64)]),
+    "mgb200_pagerank_multi": (i32, [u64, u64, vp, vp, ctypes.POINTER(RunParams), u32, u32, vp, vp, ctypes.POINTER(u64)]),
     "mgb200_partition_range": (i32, [u64, u32, u32, ctypes.POINTER(u64), ctypes.POINTER(u64)]),
     "mgb200_partition_locate": (i32, [u64, u64, u32, i32, u64, ctypes.POINTER(u32), ctypes.POINTER(u64)]),
     "mgb200_partition_label": (i32, [u64, u64, u32, i32, u32, u64, ctypes.POINTER(u64), ctypes.POINTER(u64)]),

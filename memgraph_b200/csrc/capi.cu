@@ -6,6 +6,8 @@
 // There is no CPU compute path: every entry point that needs a device fails with
 // MGB200_ERR_CUDA when none is usable.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -83,6 +85,10 @@ int validate_sizes(uint64_t n, uint32_t part_rank, uint32_t part_world) {
 // Iteration loop shared by the single- and multi-partition entry points.
 int iterate(Graph &g, const mgb200_run_params &p, mgb200_run_stats &stats) {
   MGB_CUDA(cudaSetDevice(g.device));
+  if (g.poisoned) {
+    set_error("this partition handle saw a peer time-out earlier; its barrier state is undefined -- destroy and rebuild it");
+    return MGB200_ERR_COMM;
+  }
   IterateConfig cfg{p.max_iterations, p.damping_factor, p.stop_epsilon};
   stats = mgb200_run_stats{};
   if (g.n == 0) {
@@ -107,6 +113,7 @@ int iterate(Graph &g, const mgb200_run_params &p, mgb200_run_stats &stats) {
   uint64_t launches = 0, spmv = 0;
   uint64_t it = 0;
   bool done = p.max_iterations == 0;
+  bool abort_sent = false;
   const uint64_t batch_cap = 32;
   while (!done) {
     uint64_t batch = batch_cap;
@@ -118,13 +125,20 @@ int iterate(Graph &g, const mgb200_run_params &p, mgb200_run_stats &stats) {
     MGB_CUDA(cudaMemcpyAsync(g.host_state, g.state, sizeof(IterState), cudaMemcpyDeviceToHost, g.stream));
     MGB_CUDA(cudaStreamSynchronize(g.stream));
     if (g.host_state->error) {
+      g.poisoned = true;
       set_error("multi-GPU barrier timed out waiting for a peer partition");
       return MGB200_ERR_COMM;
     }
-    done = g.host_state->done != 0 || it >= p.max_iterations;
-    if (!done && p.should_abort && p.should_abort(p.abort_user)) {
+    if (g.host_state->aborted) {  // some partition's host asked to stop: every partition left the loop in the same iteration
       set_error("aborted by the host (mgp_must_abort)");
       return MGB200_ERR_ABORTED;
+    }
+    done = g.host_state->done != 0 || it >= p.max_iterations;
+    if (!done && !abort_sent && p.should_abort && p.should_abort(p.abort_user)) {
+      // publish the request; the next iteration end turns it into a collective stop (pagerank_kernels.cu iter_end_kernel)
+      static const int one = 1;
+      MGB_CUDA(cudaMemcpyAsync(&g.state->abort_req, &one, sizeof(int), cudaMemcpyHostToDevice, g.stream));
+      abort_sent = true;
     }
   }
   rc = launch_sum_and_exchange(g);
@@ -134,6 +148,7 @@ int iterate(Graph &g, const mgb200_run_params &p, mgb200_run_stats &stats) {
   MGB_CUDA(cudaMemcpyAsync(g.host_state, g.state, sizeof(IterState), cudaMemcpyDeviceToHost, g.stream));
   MGB_CUDA(cudaStreamSynchronize(g.stream));
   if (g.host_state->error) {
+    g.poisoned = true;
     set_error("multi-GPU barrier timed out waiting for a peer partition");
     return MGB200_ERR_COMM;
   }
@@ -420,13 +435,17 @@ int mgb200_parallel_iterative_pagerank(uint64_t n, uint64_t m, const uint64_t *f
   return MGB200_OK;
 }
 
-int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
-                                             uint64_t max_iterations, double damping_factor, double stop_epsilon,
-                                             uint32_t number_of_threads, uint32_t gpu_count, const int *devices,
-                                             double *rank_out, uint64_t *iterations_out) {
-  if (gpu_count <= 1) {
-    return mgb200_parallel_iterative_pagerank(n, m, from, to, max_iterations, damping_factor, stop_epsilon,
-                                              number_of_threads, rank_out, iterations_out);
+namespace {
+int poll_flag(void *user) { return static_cast<std::atomic<int> *>(user)->load(std::memory_order_relaxed); }
+}  // namespace
+
+int mgb200_pagerank_multi(uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
+                          const mgb200_run_params *params, uint32_t number_of_threads, uint32_t gpu_count,
+                          const int *devices, double *rank_out, uint64_t *iterations_out) {
+  if (!params) return MGB200_ERR_INVALID_ARGUMENT;
+  if (params->rank_out_on_device) {
+    set_error("mgb200_pagerank_multi gathers into host memory (rank_out_on_device must be 0)");
+    return MGB200_ERR_INVALID_ARGUMENT;
   }
   if (number_of_threads == 0) {
     set_error(MGB200_MSG_ZERO_THREADS);
@@ -436,9 +455,20 @@ int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint6
     set_error("at most " + std::to_string(kMaxPeers) + " GPUs per graph");
     return MGB200_ERR_INVALID_ARGUMENT;
   }
-  if (n == 0) {
-    return mgb200_parallel_iterative_pagerank(n, m, from, to, max_iterations, damping_factor, stop_epsilon,
-                                              number_of_threads, rank_out, iterations_out);
+  if (gpu_count <= 1 || n == 0) {
+    if (n == 0)
+      return mgb200_parallel_iterative_pagerank(n, m, from, to, params->max_iterations, params->damping_factor,
+                                                params->stop_epsilon, number_of_threads, rank_out, iterations_out);
+    const char *dev_env = getenv("MGB200_DEVICE");
+    const int device = devices ? devices[0] : (dev_env ? atoi(dev_env) : 0);
+    mgb200_graph *g = nullptr;
+    int rc = mgb200_graph_create_host(device, n, m, from, to, 0, 1, &g);
+    if (rc) return rc;
+    mgb200_run_stats stats{};
+    rc = mgb200_pagerank_run(g, params, rank_out, &stats);
+    mgb200_graph_destroy(g);
+    if (!rc && iterations_out) *iterations_out = stats.iterations;
+    return rc;
   }
   std::vector<mgb200_graph *> parts(gpu_count, nullptr);
   auto destroy_all = [&]() {
@@ -459,7 +489,12 @@ int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint6
       return rc;
     }
   }
-  // one host thread per GPU: the partitions meet in device-side barriers, so they must all be launched
+  // One host thread per GPU: the partitions meet in device-side barriers, so they must all be launched.  The caller's
+  // should_abort hook may only be used from the CALLING thread (mgp_* functions are not thread-safe, mg_procedure.h:75-81),
+  // so this thread polls it while the workers run and hands the answer to them through an atomic flag; the device side
+  // turns the first partition's request into a collective stop.
+  std::atomic<int> abort_flag{0};
+  std::atomic<uint32_t> finished{0};
   std::vector<int> rcs(gpu_count, MGB200_OK);
   std::vector<std::string> messages(gpu_count);
   std::vector<std::vector<double>> ranks(gpu_count);
@@ -468,16 +503,22 @@ int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint6
   std::vector<std::thread> workers;
   for (uint32_t q = 0; q < gpu_count; ++q) {
     workers.emplace_back([&, q]() {
-      mgb200_run_params p{};
-      p.max_iterations = max_iterations;
-      p.damping_factor = damping_factor;
-      p.stop_epsilon = stop_epsilon;
+      mgb200_run_params p = *params;
+      p.should_abort = params->should_abort ? poll_flag : nullptr;
+      p.abort_user = &abort_flag;
+      p.rank_out_on_device = 0;
       const uint64_t rows = parts[q]->g.local_rows;
       ranks[q].resize(rows);
       vertices[q].resize(rows);
       rcs[q] = mgb200_pagerank_run_partition(parts[q], &p, ranks[q].data(), vertices[q].data(), &stats[q]);
       if (rcs[q]) messages[q] = mgb200_last_error();
+      finished.fetch_add(1, std::memory_order_release);
     });
+  }
+  while (finished.load(std::memory_order_acquire) < gpu_count) {
+    if (params->should_abort && !abort_flag.load(std::memory_order_relaxed) && params->should_abort(params->abort_user))
+      abort_flag.store(1, std::memory_order_relaxed);
+    std::this_thread::sleep_for(std::chrono::milliseconds(2));
   }
   for (auto &w : workers) w.join();
   destroy_all();
@@ -491,6 +532,21 @@ int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint6
     for (size_t r = 0; r < ranks[q].size(); ++r) rank_out[vertices[q][r]] = ranks[q][r];
   if (iterations_out) *iterations_out = stats[0].iterations;
   return MGB200_OK;
+}
+
+int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
+                                             uint64_t max_iterations, double damping_factor, double stop_epsilon,
+                                             uint32_t number_of_threads, uint32_t gpu_count, const int *devices,
+                                             double *rank_out, uint64_t *iterations_out) {
+  if (gpu_count <= 1) {
+    return mgb200_parallel_iterative_pagerank(n, m, from, to, max_iterations, damping_factor, stop_epsilon,
+                                              number_of_threads, rank_out, iterations_out);
+  }
+  mgb200_run_params p{};
+  p.max_iterations = max_iterations;
+  p.damping_factor = damping_factor;
+  p.stop_epsilon = stop_epsilon;
+  return mgb200_pagerank_multi(n, m, from, to, &p, number_of_threads, gpu_count, devices, rank_out, iterations_out);
 }
 
 // ---- Katz centrality (include/mgb200_katz.h; kernels in katz.cu) -----------------------------------------
@@ -658,6 +714,11 @@ int mgb200_graph_connect_peers(mgb200_graph *h, const void *const *ipc_handles, 
     g.peers.contrib[0][q] = reinterpret_cast<double *>(bytes + kFlagPageBytes);
     g.peers.contrib[1][q] = reinterpret_cast<double *>(bytes + kFlagPageBytes + g.contrib_stride);
   }
+  // a fresh connection starts every partition's barrier counter from zero (all partitions reconnect together, before
+  // any run): this is also how a set of handles recovers after a peer time-out poisoned them
+  MGB_CUDA(cudaMemset(g.window, 0, kFlagPageBytes));
+  MGB_CUDA(cudaMemset(&g.state->barrier_seq, 0, sizeof(unsigned long long)));
+  g.poisoned = false;
   g.peers_connected = true;
   return MGB200_OK;
 }

@@ -100,7 +100,8 @@ struct RowMap {
 
 // Written by iteration kernels, read by the host between batches (plain device memory).
 struct IterState {
-  unsigned long long diff_bits;   // running max |delta| of the current iteration (bits of a double >= 0)
+  unsigned long long diff_bits;   // running max |delta| of the current iteration as bits(double >= 0) + 1; 0 = no
+                                  // non-NaN delta seen yet (CheckContinueIterate finds no element > eps then)
   unsigned long long iterations;  // completed iterations (the reference's number_of_iterations)
   unsigned long long barrier_seq; // cross-GPU barrier sequence number (monotonic over the handle's life)
   double last_diff;
@@ -108,6 +109,22 @@ struct IterState {
   double rank_sum;                // global sum (NormalizeRank divisor)
   int done;                       // set when CheckContinueIterate would return false
   int error;                      // 1: peer barrier timed out
+  int abort_req;                  // written by THIS partition's host between batches: should_abort said stop
+  int aborted;                    // set on EVERY partition in the same iteration once any partition asked to abort
+};
+constexpr unsigned long long kAbortBits = ~0ull;  // published instead of the delta by a partition that wants to abort
+
+// Ticket counter of the SELL kernel's work items (pagerank_kernels.cu sell_rows_kernel).
+struct WorkQueue {
+  unsigned long long ticket;
+  unsigned int ctas_done;
+  unsigned int pad;
+};
+
+// One work item of the SELL kernel: slices [slice_begin, slice_end) and the column base of its first two slices, so a
+// warp that draws the item needs ONE 32-byte record before its first index load.
+struct WorkItem {
+  uint64_t slice_begin, slice_end, col_begin, col_end;  // columns = 32-entry columns of sell_idx (colbase units)
 };
 
 // First page of the exchange window; every slot [q] is written by peer q (remote store over NVLink).
@@ -156,6 +173,7 @@ struct Graph {
   uint64_t *seg_begin = nullptr;  // [n_seg] first edge
   uint64_t *seg_first = nullptr;  // [n_heavy + 1] first segment of each heavy row
   double *seg_partial = nullptr;  // [n_seg]
+  double *heavy_sums = nullptr;   // [n_heavy] per-row gathered sums of the current iteration
 
   // SELL class
   uint64_t n_slices = 0;
@@ -166,7 +184,11 @@ struct Graph {
   double *sell_sums = nullptr;       // [n_sell] per-row gathered sums of the current iteration
   uint32_t sell_items = 0;           // work items of the streaming kernel: contiguous slice runs, ~equal columns
   uint64_t *sell_item_begin = nullptr;  // [sell_items + 1] first slice of each item
-  std::vector<uint64_t> sell_item_begin_host;  // host copy (chunked launches of the SELL class)
+  uint32_t sell_work = 0;            // work items of sell_rows_kernel: contiguous slice runs of ~equal cost
+  uint64_t *sell_work_begin = nullptr;  // [sell_work + 1]
+  WorkItem *sell_work_items = nullptr;  // [sell_work]
+  WorkQueue *queue = nullptr;        // ticket counter (zero between launches)
+  bool sell_static = false;          // items dealt round-robin instead of drawn by ticket (small partitions)
 
   // iteration state
   double *rank = nullptr;      // [local_rows] un-normalised ranks, updated in place
@@ -180,14 +202,14 @@ struct Graph {
   PeerTable peers{};                // device pointers valid on THIS device
   void *peer_mapped[kMaxPeers] = {};  // IPC mappings to close
   bool peers_connected = false;
+  bool poisoned = false;  // a peer barrier timed out: the partitions' barrier counters may disagree; runs are refused
 
   uint64_t resident_bytes = 0;
   double build_ms = 0.0;
   cudaEvent_t ev[4] = {};
   // side stream for the SELL epilogue (overlaps the peer push with the heavy-row kernels)
   cudaStream_t stream2 = nullptr;
-  static constexpr int kMaxChunks = 8;
-  cudaEvent_t fork_evs[kMaxChunks] = {};
+  cudaEvent_t fork_ev = nullptr;
   cudaEvent_t join_ev = nullptr;
   bool overlap_epilogue = true;
   bool stream_attr_set = false;
@@ -202,13 +224,13 @@ struct Graph {
     bool multi_aware = true;     // MGB200_MULTI_AWARE=0: legacy "global label prefix is hot" on every partition
     bool force_multi_path = false;  // MGB200_FORCE_MULTI_PATH=1: run the multi-partition gather code on one GPU (measurement)
     bool stream_kernel = false;  // MGB200_SELL_KERNEL=stream
+    int sell_mode = -1;          // MGB200_SELL_MODE: 0 ticket queue, 1 static deal, -1 (default) by partition size
     bool global_order = false;   // MGB200_LABELLING=global: label = global degree order, blocks of 32 dealt (RowMap)
     bool push_mask = false;      // MGB200_PUSH_MASK=1: push a contribution only to the partitions that gather it
     bool lone_partition = false; // MGB200_LONE_PARTITION=1 (profiling only): run ONE partition of part_world without its
                                  // peers -- no stores to them, barrier of one; timings/ncu are real, ranks are NOT
     bool push_copy = false;      // MGB200_PUSH=copy (dealt contiguous ranges only)
     int idx_flags = -1;          // MGB200_IDX_FLAGS: 1 bake hotness into the indices, 0 never, -1 (default) see build_graph
-    int sell_chunks = 1;         // MGB200_SELL_CHUNKS
     unsigned long long barrier_timeout_ms = 20000;  // MGB200_BARRIER_TIMEOUT_MS
   } tun;
   // hot thresholds in LOCAL label units (label - first label of the owning partition); one definition for the

@@ -256,21 +256,34 @@ __global__ void sell_fill_kernel(uint64_t n_slices, uint64_t first_row, uint64_t
 // work items for the streaming SELL kernel: item i starts at the first slice whose column base is
 // >= i * total_cols / n_items (binary search over the slice column bases)
 __global__ void sell_items_kernel(uint32_t n_items, uint64_t n_slices, const uint64_t *colbase, uint64_t total_cols,
-                                  uint64_t *item_begin) {
+                                  uint64_t slice_cost, uint64_t *item_begin) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n_items) return;
   if (i == n_items) {
     item_begin[i] = n_slices;
     return;
   }
-  const unsigned __int128 t = static_cast<unsigned __int128>(total_cols) * i;
+  // cost of slices [0, s) = their columns + slice_cost per slice; item i starts where that reaches i/n_items of the total
+  const unsigned __int128 t = static_cast<unsigned __int128>(total_cols + slice_cost * n_slices) * i;
   const uint64_t target = static_cast<uint64_t>(t / n_items);
-  uint64_t lo = 0, hi = n_slices;  // first s in [0, n_slices] with colbase[s] >= target
+  uint64_t lo = 0, hi = n_slices;  // first s in [0, n_slices] with cost(s) >= target
   while (lo < hi) {
     const uint64_t mid = (lo + hi) >> 1;
-    if (colbase[mid] < target) lo = mid + 1; else hi = mid;
+    if (colbase[mid] + slice_cost * mid < target) lo = mid + 1; else hi = mid;
   }
   item_begin[i] = lo;
+}
+
+__global__ void work_item_kernel(uint32_t n_items, const uint64_t *item_begin, const uint64_t *colbase, WorkItem *out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  const uint64_t b = item_begin[i], e = item_begin[i + 1];
+  WorkItem w{b, e, 0, 0};
+  if (b < e) {
+    w.col_begin = colbase[b];
+    w.col_end = colbase[e];
+  }
+  out[i] = w;
 }
 
 // by_local[r] = by_label[label of this partition's local row r]  (original vertex ids, in-degrees)
@@ -352,11 +365,14 @@ void free_graph(Graph &g) {
   for (int q = 0; q < kMaxPeers; ++q)
     if (g.peer_mapped[q]) cudaIpcCloseMemHandle(g.peer_mapped[q]);
   if (g.sell_item_begin) cudaFree(g.sell_item_begin);
+  if (g.sell_work_begin) cudaFree(g.sell_work_begin);
+  if (g.sell_work_items) cudaFree(g.sell_work_items);
+  if (g.queue) cudaFree(g.queue);
   if (g.sell_sums) cudaFree(g.sell_sums);
   if (g.out_stage) cudaFree(g.out_stage);
   if (g.need_mask) cudaFree(g.need_mask);
   void *ptrs[] = {g.label_of,  g.outdeg_l,  g.local_vertex, g.heavy_ptr,    g.heavy_idx, g.seg_row,     g.seg_begin,
-                  g.seg_first, g.seg_partial, g.sell_colbase, g.sell_idx,     g.rank,      g.window,      g.state,
+                  g.seg_first, g.seg_partial, g.heavy_sums, g.sell_colbase, g.sell_idx,     g.rank,      g.window,      g.state,
                   g.sum_partials};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -365,8 +381,7 @@ void free_graph(Graph &g) {
     if (e) cudaEventDestroy(e);
   for (auto &e : g.kev)
     if (e) cudaEventDestroy(e);
-  for (auto &e : g.fork_evs)
-    if (e) cudaEventDestroy(e);
+  if (g.fork_ev) cudaEventDestroy(g.fork_ev);
   if (g.join_ev) cudaEventDestroy(g.join_ev);
   for (auto &e : g.copy_done)
     if (e) cudaEventDestroy(e);
@@ -385,7 +400,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   g.sm_count = prop.multiProcessorCount;
   MGB_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   MGB_CUDA(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
-  for (auto &e : g.fork_evs) MGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  MGB_CUDA(cudaEventCreateWithFlags(&g.fork_ev, cudaEventDisableTiming));
   MGB_CUDA(cudaEventCreateWithFlags(&g.join_ev, cudaEventDisableTiming));
   MGB_CUDA(cudaEventCreateWithFlags(&g.sell_ready_ev, cudaEventDisableTiming));
   MGB_CUDA(cudaEventCreateWithFlags(&g.heavy_ready_ev, cudaEventDisableTiming));
@@ -398,11 +413,11 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     if ((s = getenv("MGB200_FORCE_MULTI_PATH")) != nullptr) g.tun.force_multi_path = s[0] == '1';
     if ((s = getenv("MGB200_SELL_KERNEL")) != nullptr) g.tun.stream_kernel = strcmp(s, "stream") == 0;
     if ((s = getenv("MGB200_IDX_FLAGS")) != nullptr) g.tun.idx_flags = atoi(s);
+    if ((s = getenv("MGB200_SELL_MODE")) != nullptr) g.tun.sell_mode = atoi(s);
     if ((s = getenv("MGB200_LABELLING")) != nullptr) g.tun.global_order = strcmp(s, "global") == 0;
     if ((s = getenv("MGB200_PUSH_MASK")) != nullptr) g.tun.push_mask = s[0] == '1';
     if ((s = getenv("MGB200_LONE_PARTITION")) != nullptr) g.tun.lone_partition = s[0] == '1';
     if ((s = getenv("MGB200_PUSH")) != nullptr) g.tun.push_copy = strcmp(s, "copy") == 0;
-    if ((s = getenv("MGB200_SELL_CHUNKS")) != nullptr) g.tun.sell_chunks = std::max(1, atoi(s));
     if ((s = getenv("MGB200_BARRIER_TIMEOUT_MS")) != nullptr) {
       const unsigned long long ms = strtoull(s, nullptr, 10);
       if (ms) g.tun.barrier_timeout_ms = ms;
@@ -437,6 +452,8 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   MGB_CUDA(cudaMemsetAsync(g.state, 0, sizeof(IterState), st));
   MGB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&g.host_state), sizeof(IterState)));
   MGB_CUDA(keep_alloc(g, &g.sum_partials, kSumBlocks));
+  MGB_CUDA(keep_alloc(g, &g.queue, 1));
+  MGB_CUDA(cudaMemsetAsync(g.queue, 0, sizeof(WorkQueue), st));
   g.contrib_stride = ((n + 1) * sizeof(double) + 255) / 256 * 256;
   g.window_bytes = kFlagPageBytes + 2 * g.contrib_stride;
   MGB_CUDA(cudaMalloc(&g.window, g.window_bytes));
@@ -661,6 +678,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     MGB_CUDA(keep_alloc(g, &g.seg_row, g.n_seg));
     MGB_CUDA(keep_alloc(g, &g.seg_begin, g.n_seg));
     MGB_CUDA(keep_alloc(g, &g.seg_partial, g.n_seg));
+    MGB_CUDA(keep_alloc(g, &g.heavy_sums, g.n_heavy));
     segment_fill_kernel<<<blocks_for(g.n_heavy * 32, g.sm_count), kThreads, 0, st>>>(
         g.n_heavy, g.heavy_ptr, g.seg_first, g.segment_edges, g.seg_row, g.seg_begin);
   }
@@ -695,11 +713,25 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     g.sell_items = env_u32("MGB200_SELL_ITEMS", static_cast<uint32_t>(g.sm_count) * 32u);
     MGB_CUDA(keep_alloc(g, &g.sell_item_begin, static_cast<uint64_t>(g.sell_items) + 1));
     sell_items_kernel<<<(g.sell_items + 1 + kThreads - 1) / kThreads, kThreads, 0, st>>>(
-        g.sell_items, g.n_slices, g.sell_colbase, total_cols, g.sell_item_begin);
-    g.sell_item_begin_host.resize(static_cast<size_t>(g.sell_items) + 1);
-    MGB_CUDA(cudaMemcpyAsync(g.sell_item_begin_host.data(), g.sell_item_begin,
-                             g.sell_item_begin_host.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    MGB_CUDA(cudaStreamSynchronize(st));
+        g.sell_items, g.n_slices, g.sell_colbase, total_cols, 0, g.sell_item_begin);
+    // Work items of sell_rows_kernel (contiguous slice runs of ~equal cost = columns + kSliceCost per slice).
+    // Measured on scale-26 partitions (profiles/r02_sell_schedule.md): with >= 64 slices per resident warp the ticket
+    // queue over ~16 items per warp wins (whole graph 2.12 vs 2.51 ms), below that every extra run start costs more
+    // than the balance gains and ONE (or two) contiguous runs per warp, dealt statically, are fastest
+    // (1/8 partition: 0.37 vs 0.56 ms; 1/4: 0.68 vs 0.77 ms).
+    constexpr uint64_t kSliceCost = 8;
+    const uint64_t resident_warps = static_cast<uint64_t>(g.sm_count) * 32u;  // 4 CTAs x 8 warps per SM
+    const uint64_t per_warp = g.n_slices / resident_warps;
+    g.sell_static = g.tun.sell_mode >= 0 ? g.tun.sell_mode == 1 : per_warp < 64;
+    const uint64_t items_default = !g.sell_static ? resident_warps * 16 : (per_warp < 32 ? resident_warps : resident_warps * 2);
+    g.sell_work = static_cast<uint32_t>(std::min<uint64_t>(
+        g.n_slices, env_u32("MGB200_SELL_WORK_ITEMS", static_cast<uint32_t>(items_default))));
+    MGB_CUDA(keep_alloc(g, &g.sell_work_begin, static_cast<uint64_t>(g.sell_work) + 1));
+    sell_items_kernel<<<(g.sell_work + 1 + kThreads - 1) / kThreads, kThreads, 0, st>>>(
+        g.sell_work, g.n_slices, g.sell_colbase, total_cols, kSliceCost, g.sell_work_begin);
+    MGB_CUDA(keep_alloc(g, &g.sell_work_items, g.sell_work));
+    work_item_kernel<<<(g.sell_work + kThreads - 1) / kThreads, kThreads, 0, st>>>(g.sell_work, g.sell_work_begin,
+                                                                                  g.sell_colbase, g.sell_work_items);
   }
   MGB_CUDA(cudaGetLastError());
   MGB_CUDA(cudaEventRecord(g.ev[1], st));

@@ -26,7 +26,7 @@ constexpr int kBlockThreads = 256;
 constexpr int kWarpsPerBlock = kBlockThreads / 32;
 constexpr unsigned kFull = 0xffffffffu;
 #ifndef MGB_UNROLL
-#define MGB_UNROLL 8
+#define MGB_UNROLL 8   // heavy-row segments: gathers in flight per lane
 #endif
 constexpr int kUnroll = MGB_UNROLL;
 
@@ -196,32 +196,8 @@ struct RowEpilogue {
   uint32_t store_mask;     // bit q: the epilogue stores into partition q's buffer (all ones; self only under MGB200_PUSH=copy)
 };
 
-// rank_next = base + d * acc as two separately rounded operations, like the reference's
-// `rank_next[i] += damping_factor * block[i]` compiled without FMA contraction (:109-111).
-__device__ __forceinline__ double finish_row(const RowEpilogue &ep, uint64_t local_row, double acc,
-                                             uint64_t stream_pol) {
-  const double next = __dadd_rn(ep.base, __dmul_rn(ep.damping, acc));
-  const double prev = ld_stream_f64(ep.rank + local_row, stream_pol);
-  st_stream_f64(ep.rank + local_row, next, stream_pol);
-  const uint64_t label = ep.map.label_of_local(local_row);
-  const uint32_t od = ld_index(ep.outdeg + label, stream_pol);
-  // A vertex without out-edges is never a gather source, so its contribution is never read: no division,
-  // no store, and -- what matters across GPUs -- no NVLink push.  Labels are sorted by (in-degree, out-degree)
-  // descending, so these vertices are the contiguous tail of every in-degree class: whole warps skip.
-  if (od != 0) {
-    const double c = __ddiv_rn(next, static_cast<double>(od));  // :93 quotient, once per vertex
-    // push only to the partitions that have an in-edge from this vertex (graph_build.cu need_mask_kernel)
-    const uint32_t need = ep.need ? (static_cast<uint32_t>(ep.need[local_row]) | (1u << ep.self)) : 0xFFu;
-#pragma unroll
-    for (int q = 0; q < kMaxPeers; ++q) {
-      if (q < ep.world && (((need & ep.store_mask) >> q) & 1u))
-        st_stream_f64(ep.contrib_out[q] + label, c, stream_pol);  // q != self: NVLink store
-    }
-  }
-  return fabs(next - prev);
-}
-
-// max over the block of non-negative, non-NaN doubles -> one atomicMax on the bit pattern.
+// max over the block of the rows' |delta| (callers start from -1.0 = "none seen"; NaN deltas never replace it, like
+// the reference's `abs(...) > eps` is false for NaN) -> one atomicMax on bits + 1, so that 0 keeps meaning "none".
 __device__ __forceinline__ void block_max_to_state(double local_max, IterState *state) {
   __shared__ double warp_max[kWarpsPerBlock];
   for (int o = 16; o > 0; o >>= 1) {
@@ -235,7 +211,7 @@ __device__ __forceinline__ void block_max_to_state(double local_max, IterState *
     double m = warp_max[0];
     for (int w = 1; w < kWarpsPerBlock; ++w)
       if (warp_max[w] > m) m = warp_max[w];
-    if (m > 0.0) atomicMax(&state->diff_bits, static_cast<unsigned long long>(__double_as_longlong(m)));
+    if (m >= 0.0) atomicMax(&state->diff_bits, static_cast<unsigned long long>(__double_as_longlong(m)) + 1ull);
   }
 }
 
@@ -285,6 +261,8 @@ __global__ void __launch_bounds__(kBlockThreads) init_kernel(uint64_t n, uint64_
     state->rank_sum = 0.0;
     state->done = 0;
     state->error = 0;
+    state->abort_req = 0;
+    state->aborted = 0;
   }
 }
 
@@ -307,120 +285,183 @@ __global__ void __launch_bounds__(kBlockThreads) zero_refresh_kernel(double zero
 
 // ---- SELL-32 rows: one lane per row, coalesced column-major index reads -----------------------------
 
-struct SellArgs {
-  const uint64_t *colbase;
-  const uint32_t *idx;
-  uint64_t slice_begin;  // this launch covers slices [slice_begin, slice_begin + n_slices)
-  uint64_t n_slices;
-  uint64_t first_row;  // local row of slice 0, lane 0
-  uint64_t end_row;    // first local row past the SELL class
-  const double *contrib_in;
-  GatherWindow window;
-  IterState *state;
-  double *sums;  // [n_sell] per-row sums of gathered contributions (consumed by sell_epilogue_kernel)
-};
-
-// Row epilogue of the SELL class as a separate, perfectly coalesced elementwise pass.  Fusing it into
-// the gather kernels cost 2.9 ms of 5.2 ms at scale-26 (profiles/r01_attribution.md): the rank and
-// out-degree loads, the FP64 division and the stores sit at the end of every slice's dependency chain and
-// drain the warp's memory pipeline once per ~24 columns.  Split, it is ~0.2 ms of pure streaming.
-__global__ void __launch_bounds__(kBlockThreads) sell_epilogue_kernel(uint64_t first_row, uint64_t end_row,
-                                                                      const double *sums, IterState *state,
-                                                                      const RowEpilogue ep) {
+// Row epilogue as a separate, perfectly coalesced elementwise pass over rows [first_row, end_row) whose gathered sums
+// lie in sums[r - first_row]; used for the SELL class (its own kernel on the side stream) and for the heavy rows
+// (after heavy_rowsum_kernel).  History: fused into the gather kernels it cost 2.9 ms of 5.2 ms at scale-26
+// (profiles/r01_attribution.md): the rank and out-degree loads, the FP64 division and the stores sit at the end of
+// every slice's dependency chain and drain the warp's memory pipeline once per ~24 columns.  The first split version
+// walked one row per thread per trip through two dependent DRAM round trips (sums -> rank / out-degree) with
+// asm-volatile loads, which pin the issue order; this one takes kEpiRows rows per trip and issues every load of the
+// trip before the first use, as plain streaming loads (ld/st.global.cs) the compiler may hoist
+// (profiles/r02_epilogue.md: 0.28 -> 0.19 ms at scale-26, 0.26 -> 0.025 ms on a 1/8 partition).
+//
+//   rank_next = base + d * acc as two separately rounded operations, like the reference's
+//   `rank_next[i] += damping_factor * block[i]` compiled without FMA contraction (:109-111);
+//   contribution = rank_next / outdeg with an IEEE division (:93), once per vertex instead of once per edge.
+constexpr int kEpiRows = 4;
+__global__ void __launch_bounds__(kBlockThreads) row_epilogue_kernel(uint64_t first_row, uint64_t end_row,
+                                                                     const double *sums, IterState *state,
+                                                                     const RowEpilogue ep) {
   if (ld_volatile_int(&state->done)) return;
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-  const uint64_t pol = make_evict_first_policy();
-  double local_max = 0.0;
-  for (uint64_t r = first_row + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < end_row;
-       r += stride) {
-    const double d = finish_row(ep, r, ld_stream_f64(sums + (r - first_row), pol), pol);
-    if (d > local_max) local_max = d;
+  double local_max = -1.0;
+  for (uint64_t r0 = first_row + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r0 < end_row;
+       r0 += stride * kEpiRows) {
+    double acc[kEpiRows], prev[kEpiRows];
+    uint32_t od[kEpiRows], need[kEpiRows];
+    uint64_t label[kEpiRows];
+#pragma unroll
+    for (int j = 0; j < kEpiRows; ++j) {
+      const uint64_t r = r0 + j * stride;
+      const bool ok = r < end_row;
+      label[j] = ep.map.label_of_local(ok ? r : first_row);
+      acc[j] = ok ? __ldcs(sums + (r - first_row)) : 0.0;
+      prev[j] = ok ? __ldcs(ep.rank + r) : 0.0;
+      od[j] = ok ? __ldcs(ep.outdeg + label[j]) : 0u;
+      // push only to the partitions that have an in-edge from this vertex (graph_build.cu need_mask_kernel)
+      need[j] = (ok && ep.need) ? (static_cast<uint32_t>(__ldcs(ep.need + r)) | (1u << ep.self)) : 0xFFu;
+    }
+#pragma unroll
+    for (int j = 0; j < kEpiRows; ++j) {
+      const uint64_t r = r0 + j * stride;
+      if (r < end_row) {
+        const double next = __dadd_rn(ep.base, __dmul_rn(ep.damping, acc[j]));
+        __stcs(ep.rank + r, next);
+        // A vertex without out-edges is never a gather source, so its contribution is never read: no division, no
+        // store, and -- what matters across GPUs -- no NVLink push.  Labels are sorted by (in-degree, out-degree)
+        // descending, so these vertices are the contiguous tail of every in-degree class: whole warps skip.
+        if (od[j] != 0) {
+          const double c = __ddiv_rn(next, static_cast<double>(od[j]));
+          const uint32_t to = need[j] & ep.store_mask;
+#pragma unroll
+          for (int q = 0; q < kMaxPeers; ++q)
+            if (q < ep.world && ((to >> q) & 1u)) __stcs(ep.contrib_out[q] + label[j], c);  // q != self: NVLink store
+        }
+        const double d = fabs(next - prev[j]);
+        if (d > local_max) local_max = d;  // NaN never replaces it, like the reference's `abs(...) > eps`
+      }
+    }
   }
   block_max_to_state(local_max, state);
 }
 
-// Tunables (compile-time, see profiles/ for the sweep that picked the defaults)
+struct SellArgs {
+  const uint64_t *colbase;
+  const uint32_t *idx;
+  const WorkItem *work;  // [n_work] contiguous slice runs of ~equal cost, descending width (graph_build.cu)
+  uint32_t n_work;
+  WorkQueue *queue;      // ticket counter of this launch (rewound by the last CTA to leave)
+  uint32_t mode;         // 0 tickets in list order (default), 1 static round-robin (A/B baseline)
+  uint64_t first_row;    // local row of slice 0, lane 0
+  uint64_t end_row;      // first local row past the SELL class
+  const double *contrib_in;
+  GatherWindow window;
+  IterState *state;
+  double *sums;  // [n_sell] per-row sums of gathered contributions (consumed by row_epilogue_kernel)
+};
+
+// Tunables (compile-time; sweeps: profiles/r02_sell_variants.md)
+#ifndef MGB_SELL_UNROLL
+#define MGB_SELL_UNROLL 8      // columns per batch (gathers in flight per lane)
+#endif
 #ifndef MGB_SELL_MIN_BLOCKS
 #define MGB_SELL_MIN_BLOCKS 4  // resident CTAs/SM requested from ptxas (register cap = 65536 / (256 * this))
 #endif
-#ifndef MGB_SELL_PREFETCH
-#define MGB_SELL_PREFETCH 0    // 1: load the next batch of column indices before consuming the current gathers
-#endif
+constexpr int kSellUnroll = MGB_SELL_UNROLL;
 
+// SELL-32 rows: one lane per row, a warp walks a WORK ITEM = a contiguous run of slices, i.e. one contiguous span of
+// sell_idx, as ONE stream of columns: index batch k+1 is requested before the gathers of batch k are consumed, across
+// slice boundaries -- a boundary only decides where the running sum is stored.  (The first version restarted its
+// pipeline at every slice: an exposed round trip per slice, 22 per warp on a 1/8 partition, and every run of narrow
+// slices degenerated to `width` gathers in flight.)  Items have about equal cost and are handed out in descending-width
+// order through a ticket counter, so a warp that drew cheap work (or sits on an SM with the longer way to L2) simply takes
+// more; the queue is software-pipelined (record of item i+1 and ticket of item i+2 in flight while item i is gathered).
+// mode 1 deals the items round-robin instead (no atomics) -- the A/B baseline of profiles/r02_sell_tickets.md.
 template <int kPath>
 __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_kernel(const SellArgs a) {
   if (ld_volatile_int(&a.state->done)) return;
   const int lane = threadIdx.x & 31;
   const uint64_t pol = make_evict_first_policy();
   const GatherPolicy gpol = make_gather_policy(a.contrib_in, a.window);
-  const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * kWarpsPerBlock;
-  const uint64_t warp0 = static_cast<uint64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-  // Slices are sorted by width (descending), so a plain warp-strided walk gives warp 0 up to one full
-  // slice-width more columns than the last warp in EVERY pass; alternating the direction of the walk
-  // each pass (boustrophedon) cancels that skew pairwise.
-  auto slice_of = [&](uint64_t pass) -> uint64_t {
-    return pass * warps_total + ((pass & 1ull) ? (warps_total - 1 - warp0) : warp0);
+  unsigned long long static_next = static_cast<unsigned long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  const unsigned long long warps_total = static_cast<unsigned long long>(gridDim.x) * kWarpsPerBlock;
+  auto draw = [&]() -> unsigned long long {
+    if (a.mode == 1) {
+      const unsigned long long t = static_next;
+      static_next += warps_total;
+      return t;
+    }
+    return lane == 0 ? atomicAdd(&a.queue->ticket, 1ull) : 0ull;
   };
-  uint64_t c0 = 0, c1 = 0;
-  if (slice_of(0) < a.n_slices) {
-    c0 = a.colbase[a.slice_begin + slice_of(0)];
-    c1 = a.colbase[a.slice_begin + slice_of(0) + 1];
-  }
-  for (uint64_t pass = 0; pass * warps_total < a.n_slices; ++pass) {
-    const uint64_t s = slice_of(pass);
-    if (s >= a.n_slices) continue;  // only in the last, partial pass
-    const uint32_t width = static_cast<uint32_t>(c1 - c0);
-    const uint32_t *p = a.idx + c0 * kSliceRows + lane;
-    // slice descriptor of this warp's NEXT slice: issued now, consumed after this slice's gathers
-    const uint64_t s_next = slice_of(pass + 1);
-    if (s_next < a.n_slices) {
-      c0 = a.colbase[a.slice_begin + s_next];
-      c1 = a.colbase[a.slice_begin + s_next + 1];
-    }
+  // lanes 0..3 fetch the four words of an item record (one 32-byte sector)
+  auto fetch = [&](uint32_t t) -> uint64_t {
+    return (lane < 4 && t < a.n_work) ? reinterpret_cast<const uint64_t *>(a.work + t)[lane] : 0ull;
+  };
+  uint32_t t_cur = static_cast<uint32_t>(min(__shfl_sync(kFull, draw(), 0), static_cast<unsigned long long>(a.n_work)));
+  unsigned long long pending = draw();  // ticket of the item after the first
+  uint64_t rec = fetch(t_cur);
+  while (t_cur < a.n_work) {
+    const uint64_t s_begin = __shfl_sync(kFull, rec, 0), s_end = __shfl_sync(kFull, rec, 1);
+    const uint64_t col_begin = __shfl_sync(kFull, rec, 2), col_end = __shfl_sync(kFull, rec, 3);
+    // next item: its ticket was drawn one item ago; request its record now, and draw the ticket after it
+    t_cur = static_cast<uint32_t>(min(__shfl_sync(kFull, pending, 0), static_cast<unsigned long long>(a.n_work)));
+    rec = fetch(t_cur);
+    pending = draw();
+    if (s_begin >= s_end) continue;
+    // slice ends: lane l holds colbase[block + l + 1] for a block of 32 slices (one coalesced load per 32 slices)
+    uint64_t s = s_begin, s_block = s_begin;
+    uint64_t ends = (s_block + lane + 1 <= s_end) ? a.colbase[s_block + lane + 1] : col_end;
+    uint64_t slice_end = __shfl_sync(kFull, ends, 0);
+    const uint32_t *p = a.idx + col_begin * kSliceRows + lane;  // column c of the span: p[(c - col_begin) * 32]
+    const uint64_t ncols = col_end - col_begin;
     double acc = 0.0;
-    uint32_t k = 0;
-#if MGB_SELL_PREFETCH
-    uint32_t nxt[kUnroll];
-    if (width >= kUnroll) {
+    uint32_t nxt[kSellUnroll];
 #pragma unroll
-      for (int j = 0; j < kUnroll; ++j) nxt[j] = ld_index(p + static_cast<size_t>(j) * kSliceRows, pol);
-    }
-#endif
-    for (; k + kUnroll <= width; k += kUnroll) {
-      uint32_t src[kUnroll];
-      double v[kUnroll];
-#if MGB_SELL_PREFETCH
+    for (int j = 0; j < kSellUnroll; ++j)
+      if (static_cast<uint64_t>(j) < ncols) nxt[j] = ld_index(p + static_cast<size_t>(j) * kSliceRows, pol);
+    for (uint64_t k = 0; k < ncols; k += kSellUnroll) {
+      uint32_t src[kSellUnroll];
+      double v[kSellUnroll];
 #pragma unroll
-      for (int j = 0; j < kUnroll; ++j) src[j] = nxt[j];
-      if (k + 2 * kUnroll <= width) {
+      for (int j = 0; j < kSellUnroll; ++j) src[j] = nxt[j];
 #pragma unroll
-        for (int j = 0; j < kUnroll; ++j)
-          nxt[j] = ld_index(p + static_cast<size_t>(k + kUnroll + j) * kSliceRows, pol);
+      for (int j = 0; j < kSellUnroll; ++j)  // the next batch of indices travels while this batch is gathered
+        if (k + kSellUnroll + j < ncols) nxt[j] = ld_index(p + static_cast<size_t>(k + kSellUnroll + j) * kSliceRows, pol);
+#pragma unroll
+      for (int j = 0; j < kSellUnroll; ++j)
+        if (k + j < ncols) v[j] = ld_contrib_at<kPath>(a.contrib_in, src[j], gpol, a.window);
+#pragma unroll
+      for (int j = 0; j < kSellUnroll; ++j) {
+        if (k + j < ncols) {
+          acc += v[j];  // fixed order inside a row: ascending source label
+          const uint64_t col_next = col_begin + k + j + 1;
+          while (col_next == slice_end && s < s_end) {  // (a zero-width slice would store 0 for its rows right here)
+            const uint64_t row = a.first_row + s * kSliceRows + lane;
+            if (row < a.end_row) a.sums[row - a.first_row] = acc;  // epilogue runs as its own elementwise kernel
+            acc = 0.0;
+            ++s;
+            if (s < s_end) {
+              if (s - s_block == 32) {
+                s_block = s;
+                ends = (s_block + lane + 1 <= s_end) ? a.colbase[s_block + lane + 1] : col_end;
+              }
+              slice_end = __shfl_sync(kFull, ends, static_cast<int>(s - s_block));
+            }
+          }
+        }
       }
-#else
-#pragma unroll
-      for (int j = 0; j < kUnroll; ++j) src[j] = ld_index(p + static_cast<size_t>(k + j) * kSliceRows, pol);
-#endif
-#pragma unroll
-      for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib_at<kPath>(a.contrib_in, src[j], gpol, a.window);
-#pragma unroll
-      for (int j = 0; j < kUnroll; ++j) acc += v[j];  // fixed order: ascending source label
     }
-    if (k < width) {
-      uint32_t src[kUnroll];
-      double v[kUnroll];
-#pragma unroll
-      for (int j = 0; j < kUnroll; ++j)
-        if (k + j < width) src[j] = ld_index(p + static_cast<size_t>(k + j) * kSliceRows, pol);
-#pragma unroll
-      for (int j = 0; j < kUnroll; ++j)
-        if (k + j < width) v[j] = ld_contrib_at<kPath>(a.contrib_in, src[j], gpol, a.window);
-#pragma unroll
-      for (int j = 0; j < kUnroll; ++j)
-        if (k + j < width) acc += v[j];
+  }
+  if (a.mode == 1) return;
+  // the last CTA to leave rewinds the queue for the next launch (every ticket of this launch has been drawn by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int left = atomicAdd(&a.queue->ctas_done, 1u);
+    if (left == gridDim.x - 1) {
+      a.queue->ticket = 0ull;
+      a.queue->ctas_done = 0u;
+      __threadfence();
     }
-    const uint64_t row = a.first_row + (a.slice_begin + s) * kSliceRows + lane;
-    if (row < a.end_row) a.sums[row - a.first_row] = acc;  // epilogue runs as its own elementwise kernel
   }
 }
 
@@ -435,13 +476,13 @@ struct HeavyArgs {
   const uint64_t *seg_begin;
   const uint64_t *seg_first;
   double *seg_partial;
+  double *row_sums;  // [n_heavy]
   uint64_t n_seg;
   uint64_t n_heavy;
   uint32_t segment_edges;
   const double *contrib_in;
   GatherWindow window;
   IterState *state;
-  RowEpilogue ep;
 };
 
 #ifndef MGB_HEAVY_MIN_BLOCKS
@@ -483,24 +524,20 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_HEAVY_MIN_BLOCKS) heavy_seg
   }
 }
 
-__global__ void __launch_bounds__(kBlockThreads) heavy_finish_kernel(const HeavyArgs a) {
+// per heavy row: segment partials summed in segment order (lane-strided, fixed shuffle tree) -> row_sums[r];
+// the row epilogue then runs as row_epilogue_kernel over [0, n_heavy)
+__global__ void __launch_bounds__(kBlockThreads) heavy_rowsum_kernel(const HeavyArgs a) {
   if (ld_volatile_int(&a.state->done)) return;
   const int lane = threadIdx.x & 31;
   const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * kWarpsPerBlock;
   const uint64_t warp0 = static_cast<uint64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-  double local_max = 0.0;
-  const uint64_t pol = make_evict_first_policy();
   for (uint64_t r = warp0; r < a.n_heavy; r += warps_total) {
     const uint64_t s0 = a.seg_first[r], s1 = a.seg_first[r + 1];
     double acc = 0.0;
     for (uint64_t s = s0 + lane; s < s1; s += 32) acc += a.seg_partial[s];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(kFull, acc, o);
-    if (lane == 0) {
-      const double d = finish_row(a.ep, r, acc, pol);
-      if (d > local_max) local_max = d;
-    }
+    if (lane == 0) a.row_sums[r] = acc;
   }
-  block_max_to_state(local_max, a.state);
 }
 
 // ---- cross-partition barrier over the flag pages (P == 1: degenerates to nothing) ---------------------
@@ -554,8 +591,12 @@ __global__ void iter_end_kernel(const IterEndArgs a) {
   IterState *st = a.bar.state;
   if (ld_volatile_int(&st->done)) return;
   const int lane = threadIdx.x & 31;
-  unsigned long long bits = st->diff_bits;
+  unsigned long long bits = st->diff_bits;  // bits(max delta) + 1, 0 = none
   if (a.extra_diff_bits > bits) bits = a.extra_diff_bits;
+  // Abort is a COLLECTIVE decision: a partition whose host asked to stop publishes kAbortBits instead of its delta;
+  // the max-reduce hands it to everyone, so all partitions leave the loop in the same iteration and their barrier
+  // counters stay in step (a partition that returned on its own would leave the others waiting, then run ahead).
+  if (ld_volatile_int(&st->abort_req)) bits = kAbortBits;
   bool ok = true;
   unsigned long long seq = st->barrier_seq;
   if (a.bar.world > 1) {
@@ -571,13 +612,17 @@ __global__ void iter_end_kernel(const IterEndArgs a) {
   }
   if (lane == 0) {
     st->barrier_seq = seq;
-    const double diff = __longlong_as_double(static_cast<long long>(bits));
+    const bool abort_all = bits == kAbortBits;
+    const bool any_delta = bits != 0ull && !abort_all;
+    const double diff = any_delta ? __longlong_as_double(static_cast<long long>(bits - 1ull)) : 0.0;
     st->iterations += 1ull;
     st->last_diff = diff;
-    const bool cont = (st->iterations != a.max_iterations) && (diff > a.eps);
+    // :138-150 -- continue iff the cap is not reached and SOME element has |delta| > eps (all-NaN: none has)
+    const bool cont = (st->iterations != a.max_iterations) && any_delta && (diff > a.eps);
     st->diff_bits = 0ull;
     if (!ok) st->error = 1;
-    if (!cont || !ok) st->done = 1;
+    if (abort_all) st->aborted = 1;
+    if (!cont || !ok || abort_all) st->done = 1;
   }
 }
 
@@ -825,25 +870,20 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     SellArgs s{};
     s.colbase = g.sell_colbase;
     s.idx = g.sell_idx;
-    s.slice_begin = 0;
-    s.n_slices = g.n_slices;
+    s.work = g.sell_work_items;
+    s.n_work = g.sell_work;
+    s.queue = g.queue;
+    s.mode = g.sell_static ? 1u : 0u;
     s.first_row = g.n_heavy;
     s.end_row = g.n_heavy + g.n_sell;
     s.contrib_in = contrib_in;
     s.window = make_window(g);
     s.state = g.state;
     s.sums = g.sell_sums;
-    // The SELL class can run as `chunks` launches over contiguous slice ranges of ~equal column counts, with the
-    // epilogue (+ NVLink push) of chunk c forked to the side stream as soon as chunk c's sums exist
-    // (MGB200_SELL_CHUNKS).  Default 1: at 2/4/8 GPUs the extra launches cost more than the earlier push saves.
-    // "rows" (default): warp-per-slice loop, gathers through LDG; "stream": TMA index ring + LDGSTS gathers
+    // "rows" (default): ticketed warp-per-slice kernel, gathers through LDG; "stream": TMA index ring + LDGSTS gathers
     // (sell_stream.cuh) -- correct, but measured slower (3.4 vs 2.4 ms at scale-26, profiles/r01_stream_vs_rows.md)
     const bool stream_kernel = g.tun.stream_kernel && g.sell_items > 0;
-    int chunks = 1;  // measured: no gain from chunking at 2/4/8 GPUs (profiles/r01_multi_gpu.md)
-    if (!stream_kernel && g.overlap_epilogue && !g.sell_item_begin_host.empty())
-      chunks = std::max(1, std::min(g.tun.sell_chunks, Graph::kMaxChunks));
     cudaStream_t es = g.overlap_epilogue ? g.stream2 : g.stream;
-    const int egrid_full = grid_for(g, reinterpret_cast<const void *>(sell_epilogue_kernel));
     MGB_CUDA(tick(Graph::kClsSell, 0, g.stream));
     if (stream_kernel) {
       if (!g.stream_attr_set) {  // per device, so per graph handle
@@ -864,42 +904,29 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
       t.sums = g.sell_sums;
       const int sgrid = static_cast<int>(std::min<uint64_t>(g.sm_count, ceil_div(g.sell_items, kStreamWarps)));
       sell_stream_kernel<<<sgrid, kStreamThreads, kStreamSmemBytes, g.stream>>>(t);
+    } else {
+      void (*const sell_fn)(SellArgs) = s.window.path == kPathFlags    ? sell_rows_kernel<kPathFlags>
+                                        : s.window.path == kPathLookup ? sell_rows_kernel<kPathLookup>
+                                                                       : sell_rows_kernel<kPathRange>;
+      const int grid = static_cast<int>(std::min(
+          static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_fn))), ceil_div(g.sell_work, kWarpsPerBlock)));
+      sell_fn<<<grid, kBlockThreads, 0, g.stream>>>(s);
     }
-    void (*const sell_fn)(SellArgs) = s.window.path == kPathFlags    ? sell_rows_kernel<kPathFlags>
-                                      : s.window.path == kPathLookup ? sell_rows_kernel<kPathLookup>
-                                                                     : sell_rows_kernel<kPathRange>;
-    const void *fn = reinterpret_cast<const void *>(sell_fn);
-    const int grid_full = grid_for(g, fn);
-    for (int c = 0; c < chunks; ++c) {
-      uint64_t sb = 0, se = g.n_slices;
-      if (chunks > 1) {
-        sb = g.sell_item_begin_host[static_cast<size_t>(c) * g.sell_items / chunks];
-        se = g.sell_item_begin_host[static_cast<size_t>(c + 1) * g.sell_items / chunks];
-      }
-      if (!stream_kernel && se > sb) {
-        s.slice_begin = sb;
-        s.n_slices = se - sb;
-        const int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_full), ceil_div(se - sb, kWarpsPerBlock)));
-        sell_fn<<<grid, kBlockThreads, 0, g.stream>>>(s);
-        ++launches;
-      }
-      if (c == chunks - 1) MGB_CUDA(tick(Graph::kClsSell, 1, g.stream));
-      if (g.overlap_epilogue) {
-        MGB_CUDA(cudaEventRecord(g.fork_evs[c], g.stream));
-        MGB_CUDA(cudaStreamWaitEvent(g.stream2, g.fork_evs[c], 0));
-        forked = true;
-      }
-      const uint64_t r0 = s.first_row + sb * kSliceRows;
-      const uint64_t r1 = std::min<uint64_t>(s.end_row, s.first_row + se * kSliceRows);
-      if (r1 > r0) {
-        const int egrid = static_cast<int>(std::min(static_cast<uint64_t>(egrid_full), ceil_div(r1 - r0, kBlockThreads)));
-        if (c == 0) MGB_CUDA(tick(Graph::kClsSellEpi, 0, es));
-        sell_epilogue_kernel<<<egrid, kBlockThreads, 0, es>>>(r0, r1, g.sell_sums + (r0 - s.first_row), g.state, ep);
-        ++launches;
-      }
-      if (c == chunks - 1) MGB_CUDA(tick(Graph::kClsSellEpi, 1, es));
+    ++launches;
+    MGB_CUDA(tick(Graph::kClsSell, 1, g.stream));
+    // the epilogue (+ NVLink push to the peers) of the SELL rows runs on the side stream, next to the heavy-row kernels
+    if (g.overlap_epilogue) {
+      MGB_CUDA(cudaEventRecord(g.fork_ev, g.stream));
+      MGB_CUDA(cudaStreamWaitEvent(g.stream2, g.fork_ev, 0));
+      forked = true;
     }
-    if (stream_kernel) ++launches;
+    const int egrid = static_cast<int>(
+        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(row_epilogue_kernel))),
+                 ceil_div(g.n_sell, kBlockThreads * kEpiRows)));
+    MGB_CUDA(tick(Graph::kClsSellEpi, 0, es));
+    row_epilogue_kernel<<<egrid, kBlockThreads, 0, es>>>(s.first_row, s.end_row, g.sell_sums, g.state, ep);
+    MGB_CUDA(tick(Graph::kClsSellEpi, 1, es));
+    ++launches;
     if (push_copy && g.n_sell > 0) {  // the SELL rows' slice is final once the epilogue kernel has run
       MGB_CUDA(cudaEventRecord(g.sell_ready_ev, es));
       const int crc = enqueue_peer_copies(g, out_parity, g.row_lo + g.n_heavy, g.n_sell, g.sell_ready_ev, copy_used);
@@ -921,8 +948,8 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     h.segment_edges = g.segment_edges;
     h.contrib_in = contrib_in;
     h.window = make_window(g);
+    h.row_sums = g.heavy_sums;
     h.state = g.state;
-    h.ep = ep;
     void (*const heavy_fn)(HeavyArgs) = h.window.path == kPathFlags    ? heavy_segments_kernel<kPathFlags>
                                         : h.window.path == kPathLookup ? heavy_segments_kernel<kPathLookup>
                                                                        : heavy_segments_kernel<kPathRange>;
@@ -932,11 +959,16 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     heavy_fn<<<grid, kBlockThreads, 0, g.stream>>>(h);
     MGB_CUDA(tick(Graph::kClsHeavySeg, 1, g.stream));
     grid = static_cast<int>(
-        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_finish_kernel))),
+        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_rowsum_kernel))),
                  ceil_div(g.n_heavy, kWarpsPerBlock)));
     MGB_CUDA(tick(Graph::kClsHeavyFin, 0, g.stream));
-    heavy_finish_kernel<<<grid, kBlockThreads, 0, g.stream>>>(h);
+    heavy_rowsum_kernel<<<grid, kBlockThreads, 0, g.stream>>>(h);
+    grid = static_cast<int>(
+        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(row_epilogue_kernel))),
+                 ceil_div(g.n_heavy, kBlockThreads * kEpiRows)));
+    row_epilogue_kernel<<<grid, kBlockThreads, 0, g.stream>>>(0, g.n_heavy, g.heavy_sums, g.state, ep);
     MGB_CUDA(tick(Graph::kClsHeavyFin, 1, g.stream));
+    ++launches;
     launches += 2;
     if (push_copy && g.n_heavy > 0) {
       MGB_CUDA(cudaEventRecord(g.heavy_ready_ev, g.stream));
@@ -954,9 +986,14 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
   e.max_iterations = cfg.max_iterations;
   e.eps = cfg.eps;
   e.extra_diff_bits = 0ull;
-  if (it == 0 && g.any_zero_rows) {
-    const double zd = fabs(zero_row_rank(g, cfg) - 1.0 / static_cast<double>(g.n));
-    if (zd > 0.0) memcpy(&e.extra_diff_bits, &zd, sizeof(zd));  // NaN / 0 contribute nothing, like the per-row test
+  if (g.any_zero_rows) {
+    // the zero rows are elements of the reference's stop test too: |(1-d)/N - 1/N| in iteration 0, exactly 0 afterwards
+    const double zr = zero_row_rank(g, cfg);
+    const double zd = it == 0 ? fabs(zr - 1.0 / static_cast<double>(g.n)) : fabs(zr - zr);
+    if (zd >= 0.0) {  // NaN contributes nothing, like the per-row test; same bits + 1 encoding as the rows' deltas
+      memcpy(&e.extra_diff_bits, &zd, sizeof(zd));
+      e.extra_diff_bits += 1ull;
+    }
   }
   MGB_CUDA(tick(Graph::kClsIterEnd, 0, g.stream));
   iter_end_kernel<<<1, 32, 0, g.stream>>>(e);
@@ -979,8 +1016,10 @@ int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count) 
     SellArgs s{};
     s.colbase = g.sell_colbase;
     s.idx = g.sell_idx;
-    s.slice_begin = 0;
-    s.n_slices = g.n_slices;
+    s.work = g.sell_work_items;
+    s.n_work = g.sell_work;
+    s.queue = g.queue;
+    s.mode = g.sell_static ? 1u : 0u;
     s.first_row = g.n_heavy;
     s.end_row = g.n_heavy + g.n_sell;
     s.contrib_in = vec_in;
@@ -991,7 +1030,7 @@ int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count) 
                                       : window.path == kPathLookup ? sell_rows_kernel<kPathLookup>
                                                                    : sell_rows_kernel<kPathRange>;
     const int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_fn))),
-                                               ceil_div(g.n_slices, kWarpsPerBlock)));
+                                               ceil_div(g.sell_work, kWarpsPerBlock)));
     sell_fn<<<grid, kBlockThreads, 0, g.stream>>>(s);
     ++launches;
   }
@@ -1053,9 +1092,9 @@ int launch_write_ranks_local(Graph &g, double *d_rank_out, uint32_t *d_vertex_ou
 
 int kernel_occupancy_report(Graph &g, char *buf, size_t cap) {
   int a = 0, b = 0, c = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sell_rows_kernel<false>, kBlockThreads, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, heavy_segments_kernel<false>, kBlockThreads, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, heavy_finish_kernel, kBlockThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sell_rows_kernel<kPathRange>, kBlockThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, heavy_segments_kernel<kPathRange>, kBlockThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, heavy_rowsum_kernel, kBlockThreads, 0);
   snprintf(buf, cap, "sm=%d blocks/SM: sell=%d heavy_seg=%d heavy_fin=%d (block=%d threads)", g.sm_count, a, b, c,
            kBlockThreads);
   return MGB200_OK;

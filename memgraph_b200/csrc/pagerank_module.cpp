@@ -45,14 +45,19 @@ std::vector<double> ComputeRanks(const HostGraph &hg, mgp_graph *graph, int64_t 
   const uint64_t n = hg.gid_of_dense.size();
   std::vector<double> ranks(n);
   if (n == 0) return ranks;
+  mgb200_run_params params{};
+  params.max_iterations = static_cast<uint64_t>(max_iterations);  // int64 -> size_t wrap, reference :95
+  params.damping_factor = damping_factor;
+  params.stop_epsilon = stop_epsilon;
+  params.should_abort = AbortTrampoline;  // polled between iteration batches, from this thread only
+  params.abort_user = graph;
   // MGB200_GPUS=P (2..8): vertex-partition the call over GPUs 0..P-1 (device-side exchange over NVLink)
   const char *gpus_env = std::getenv("MGB200_GPUS");
   const int gpus = gpus_env ? std::atoi(gpus_env) : 1;
   if (gpus > 1) {
     uint64_t iterations = 0;
-    const int rc = mgb200_parallel_iterative_pagerank_multi(
-        n, hg.from.size(), hg.from.data(), hg.to.data(), static_cast<uint64_t>(max_iterations), damping_factor,
-        stop_epsilon, threads, static_cast<uint32_t>(gpus), nullptr, ranks.data(), &iterations);
+    const int rc = mgb200_pagerank_multi(n, hg.from.size(), hg.from.data(), hg.to.data(), &params, threads,
+                                         static_cast<uint32_t>(gpus), nullptr, ranks.data(), &iterations);
     if (rc != MGB200_OK) throw ModuleError(mgb200_last_error());
     return ranks;
   }
@@ -61,12 +66,6 @@ std::vector<double> ComputeRanks(const HostGraph &hg, mgp_graph *graph, int64_t 
   mgb200_graph *dg = nullptr;
   int rc = mgb200_graph_create_host(device, n, hg.from.size(), hg.from.data(), hg.to.data(), 0, 1, &dg);
   if (rc != MGB200_OK) throw ModuleError(mgb200_last_error());
-  mgb200_run_params params{};
-  params.max_iterations = static_cast<uint64_t>(max_iterations);  // int64 -> size_t wrap, reference :95
-  params.damping_factor = damping_factor;
-  params.stop_epsilon = stop_epsilon;
-  params.should_abort = AbortTrampoline;
-  params.abort_user = graph;
   mgb200_run_stats stats{};
   rc = mgb200_pagerank_run(dg, &params, ranks.data(), &stats);
   const std::string message = rc != MGB200_OK ? mgb200_last_error() : "";
