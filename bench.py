@@ -400,6 +400,43 @@ def run_b200_arm(args):
                "api": "mgb200_pagerank_run_partition(graph, params, host_rank_out, host_vertex_out) on every rank",
                "rank_sum_check": float(sm.item())}
 
+    # N > 1: rank parity against the single-GPU result on the same graph, outside the timed region.  Every rank drops
+    # its (vertex, rank) slice into a full-length vector (disjoint slices, summed over NVLink), rank 0 rebuilds the
+    # WHOLE graph as one partition on its own GPU, runs the same call and compares all N ranks.
+    parity = None
+    if world > 1 and not args.no_parity:
+        import torch
+        dev = torch.device("cuda", device)
+        full = torch.zeros(n, dtype=torch.float64, device=dev)
+        idx = torch.from_numpy(host_vtx[:local_rows].astype(np.int64)).to(dev)
+        full[idx] = torch.from_numpy(host_out[:local_rows]).to(dev)
+        owned = torch.zeros(n, dtype=torch.int32, device=dev)
+        owned[idx] = 1
+        dist.all_reduce(full)
+        dist.all_reduce(owned)
+        if rank == 0:
+            t0 = time.perf_counter()
+            d_from = dev_alloc(N, lib, device, 4 * m)
+            d_to = dev_alloc(N, lib, device, 4 * m)
+            mg.rmat_edges_device(scale, m, d_from, d_to, seed=SEED, device=device)
+            g1 = mg.PageRankGraph.from_device(n, m, d_from, d_to, device=device, part_rank=0, part_world=1)
+            lib.mgb200_device_free(device, d_from)
+            lib.mgb200_device_free(device, d_to)
+            single = torch.empty(n, dtype=torch.float64, device=dev)
+            p1, _cb1 = make_params(ITERATIONS, DAMPING, 0.0, on_device=True)
+            st1 = N.RunStatsC()
+            _check(lib.mgb200_pagerank_run(g1.handle, ctypes.byref(p1), single.data_ptr(), ctypes.byref(st1)))
+            g1.close()
+            rel = ((full - single).abs() / single).max()
+            parity = {"max_rel_vs_n1": float(rel.item()), "vertices_checked": n,
+                      "every_vertex_owned_once": bool((owned == 1).all().item()),
+                      "iterations_n1": int(st1.iterations), "iterations_partitioned": int(iters),
+                      "how": "rank 0 rebuilt the whole graph as ONE partition on its GPU after the timed region and "
+                             "compared all ranks of the partitioned run with it", "seconds": time.perf_counter() - t0}
+            del single
+        del full, owned, idx
+        dist.barrier()
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -448,7 +485,7 @@ def run_b200_arm(args):
                    "heavy_rows": info["heavy_rows"], "heavy_edges": info["heavy_edges"], "sell_rows": info["sell_rows"],
                    "sell_entries": info["sell_entries"], "zero_rows": info["zero_rows"]},
         "ms_per_iteration": total_ms / args.steps / ITERATIONS,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "gpu_launches": launches, "clocks": clocks,
         "kernel_ms_per_iteration": {k: float(v) / (args.steps * ITERATIONS) for k, v in zip(CLASS_NAMES, class_ms)},
     }
     emit(line)
@@ -509,6 +546,7 @@ def main():
     ap.add_argument("--cpu-scale", type=int, default=int(os.environ.get("MGB200_CPU_SCALE", "24")),
                     help="RMAT scale of the bounded CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the comparison with the single-GPU result")
     ap.add_argument("--workload", default="pagerank", choices=["pagerank", "bfs"],
                     help="pagerank (the BASELINE metric, default) or bfs (the next path, config #5)")
     ap.add_argument("--quick", action="store_true", help="sweep mode: device-resident timing only, compact JSON")

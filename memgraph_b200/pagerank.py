@@ -183,12 +183,12 @@ class PageRankGraph:
         _check(N.lib().mgb200_graph_connect_peers(self._h, harr, garr))
 
     def run_partition(self, max_iterations=100, damping_factor=0.85, stop_epsilon=1e-5, time_spmv_kernel=False,
-                      out_device_ptr=None):
+                      out_device_ptr=None, should_abort=None):
         """Every partition calls this concurrently.  Returns (ranks, vertices, RunStats) for the rows this
         partition owns: normalised ranks and the ORIGINAL vertex id of each (None, None when
         ``out_device_ptr`` receives the ranks on the device)."""
         p, _cb = make_params(max_iterations, damping_factor, stop_epsilon, out_device_ptr is not None,
-                             time_spmv_kernel)
+                             time_spmv_kernel, should_abort)
         st = N.RunStatsC()
         rows = self.info["local_rows"]
         if out_device_ptr is not None:

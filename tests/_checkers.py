@@ -110,6 +110,25 @@ class Oracle:
         return f, t
 
 
+def pull_oracle_pagerank(n, frm, to, max_iterations=100, damping_factor=0.85, stop_epsilon=1e-5, threads=None):
+    """oracle/pagerank_pull_oracle.c: the multi-threaded pull-form checker for graphs too big for Oracle (validated
+    against it in tests/test_oracle.py).  Returns (ranks, iterations)."""
+    if not os.path.exists(ORACLE_SO):
+        build_checkers()
+    L = ctypes.CDLL(ORACLE_SO)
+    L.oracle_pull_pagerank.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                       ctypes.c_double, ctypes.c_double, ctypes.c_uint32, ctypes.c_void_p,
+                                       ctypes.POINTER(ctypes.c_uint64)]
+    frm, to = _u64(frm), _u64(to)
+    out = np.zeros(n, dtype=np.float64)
+    it = ctypes.c_uint64(0)
+    rc = L.oracle_pull_pagerank(n, len(frm), frm.ctypes.data, to.ctypes.data, max_iterations & (2**64 - 1), damping_factor,
+                                stop_epsilon, threads or min(os.cpu_count() or 1, 128), out.ctypes.data, ctypes.byref(it))
+    if rc:
+        raise OracleError(f"oracle_pull_pagerank failed: {rc}")
+    return out, it.value
+
+
 class Reference:
     """oracle/_ref/libpagerank_ref.so -- the reference's own pagerank.cpp behind oracle/ref_shim.cpp."""
 

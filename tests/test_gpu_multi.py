@@ -110,3 +110,48 @@ def test_one_call_multi_gpu_and_module_env(monkeypatch):
         nodes, ranks = module.call(g, 25, 0.85, 0.0, 1)
     order, exp, _ = oracle_through_module_semantics(oracle, gids, src, dst, max_iterations=25, stop_epsilon=0.0)
     assert np.array_equal(nodes, order) and float(np.max(np.abs(ranks - exp) / exp)) < REL_TOL
+
+
+def test_abort_is_collective_and_handles_stay_usable():
+    """one partition's host asks to abort -> EVERY partition leaves the loop in the same iteration with
+    MGB200_ERR_ABORTED (no partition waits for a peer that already returned), and the same handles then run a normal
+    call to the correct result (barrier counters still in step)."""
+    if _device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import memgraph_b200 as mg
+    from memgraph_b200 import _native as N
+    scale, world = 16, 2
+    n, m = 1 << scale, 16 << scale
+    f, t = mg.rmat_edges_host(scale, m)
+    graphs = [mg.PageRankGraph.from_arrays(n, f, t, device=q, part_rank=q, part_world=world) for q in range(world)]
+    for g in graphs:
+        g.connect_peers(local_graphs=graphs)
+    outcome = [None] * world
+
+    def work(q, abort):
+        try:
+            # enough iterations for several 32-iteration batches; stop_epsilon < 0 never converges
+            outcome[q] = ("ok", graphs[q].run_partition(max_iterations=100000, stop_epsilon=-1.0,
+                                                        should_abort=(lambda: True) if abort else None))
+        except mg.MgB200Error as e:
+            outcome[q] = ("err", e)
+
+    threads = [threading.Thread(target=work, args=(q, q == 1)) for q in range(world)]
+    [th.start() for th in threads]
+    [th.join(timeout=120) for th in threads]
+    assert all(o is not None and o[0] == "err" and o[1].code == N.ERR_ABORTED for o in outcome), outcome
+    # same handles, normal run
+    results = [None] * world
+    def work2(q):
+        results[q] = graphs[q].run_partition(max_iterations=20, stop_epsilon=0.0)
+    threads = [threading.Thread(target=work2, args=(q,)) for q in range(world)]
+    [th.start() for th in threads]
+    [th.join(timeout=120) for th in threads]
+    out = np.full(n, np.nan)
+    for ranks, verts, st in results:
+        assert st.iterations == 20
+        out[verts.astype(np.int64)] = ranks
+    for g in graphs:
+        g.close()
+    ref, _ = Oracle().pagerank(n, f, t, max_iterations=20, stop_epsilon=0.0)
+    assert float(np.max(np.abs(out - ref) / ref)) < REL_TOL
