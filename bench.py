@@ -228,6 +228,92 @@ def dev_alloc(N, lib, device, nbytes):
     return p
 
 
+def measure_e2e_call(args, mg, N, lib, device, scale, n, m, host_out):
+    import torch
+    from memgraph_b200.pagerank import _check
+    out = {}
+    # the box's pinned H2D rate, for scale: 1 GiB, best of 3
+    pin = torch.empty(1 << 28, dtype=torch.int32, pin_memory=True)
+    dst = torch.empty(1 << 28, dtype=torch.int32, device=f"cuda:{device}")
+    best = 1e9
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dst.copy_(pin, non_blocking=True)
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    out["pcie_pinned_h2d_gbs"] = (1 << 30) / best / 1e9
+    del pin, dst
+    # host COO of the benchmark graph: generated on the device (same bytes as the timed graph), copied back
+    d_from = dev_alloc(N, lib, device, 4 * m)
+    d_to = dev_alloc(N, lib, device, 4 * m)
+    mg.rmat_edges_device(scale, m, d_from, d_to, seed=SEED, device=device)
+    f32 = np.empty(m, dtype=np.uint32)
+    t32 = np.empty(m, dtype=np.uint32)
+    _check(lib.mgb200_copy_to_host(device, f32.ctypes.data, d_from, 4 * m))
+    _check(lib.mgb200_copy_to_host(device, t32.ctypes.data, d_to, 4 * m))
+    lib.mgb200_device_free(device, d_from)
+    lib.mgb200_device_free(device, d_to)
+
+    def one_shot(create, f, t, label, bytes_per_edge):
+        res = None
+        for _ in range(2):  # first call allocates the process-wide pinned staging
+            h = N.vp()
+            t0 = time.perf_counter()
+            _check(create(device, n, m, f.ctypes.data, t.ctypes.data, 0, 1, ctypes.byref(h)))
+            t1 = time.perf_counter()
+            info = N.GraphInfo()
+            _check(lib.mgb200_graph_get_info(h, ctypes.byref(info)))
+            p, _cb = make_params_e2e()
+            st = N.RunStatsC()
+            _check(lib.mgb200_pagerank_run(h, ctypes.byref(p), host_out.ctypes.data, ctypes.byref(st)))
+            t2 = time.perf_counter()
+            lib.mgb200_graph_destroy(h)
+            t3 = time.perf_counter()
+            res = {"seconds": t3 - t0, "edges_per_s": m * ITERATIONS / (t3 - t0), "create_s": t1 - t0,
+                   "upload_ms": info.upload_ms, "device_build_ms": info.build_ms, "run_s": t2 - t1, "destroy_s": t3 - t2,
+                   "h2d_bytes": 8 * m, "h2d_gbs_during_upload": 8 * m / (info.upload_ms * 1e-3) / 1e9,
+                   "host_bytes_read_per_edge": bytes_per_edge, "d2h_bytes": 8 * n, "rank_sum_check": float(host_out[:n].sum())}
+        out[label] = res
+
+    from memgraph_b200.pagerank import make_params
+    make_params_e2e = lambda: make_params(ITERATIONS, DAMPING, 0.0)
+    one_shot(lib.mgb200_graph_create_host_u32, f32, t32, "one_shot_u32", 8)
+    f64 = f32.astype(np.uint64)
+    t64 = t32.astype(np.uint64)
+    del f32, t32
+    one_shot(lib.mgb200_graph_create_host, f64, t64, "one_shot_u64", 16)
+    del f64, t64
+    out["h2d_fraction_of_pinned_rate"] = {k: out[k]["h2d_gbs_during_upload"] / out["pcie_pinned_h2d_gbs"]
+                                          for k in ("one_shot_u32", "one_shot_u64")}
+    # the drop-in module through the mgp ABI (fake host = tests' restatement of the engine side)
+    try:
+        sys.path.insert(0, os.path.join(REPO, "tests"))
+        import _fakehost as fh
+        ms = min(scale, int(os.environ.get("MGB200_MODULE_E2E_SCALE", "20")))
+        mn, mm = 1 << ms, EDGE_FACTOR << ms
+        f, t = mg.rmat_edges_host(ms, mm, seed=SEED)
+        gids = np.arange(mn, dtype=np.int64)
+        with fh.Module(fh.MODULE_SO) as module, fh.Graph(gids, f.astype(np.int64), t.astype(np.int64)) as g:
+            module.call(g, ITERATIONS, DAMPING, 0.0, 1)
+            t0 = time.perf_counter()
+            nodes, ranks = module.call(g, ITERATIONS, DAMPING, 0.0, 1)
+            dt = time.perf_counter() - t0
+            os.environ["MGB200_GRAPH_CACHE"] = "1"
+            module.call(g, ITERATIONS, DAMPING, 0.0, 1)
+            t0 = time.perf_counter()
+            module.call(g, ITERATIONS, DAMPING, 0.0, 1)
+            dtc = time.perf_counter() - t0
+            os.environ.pop("MGB200_GRAPH_CACHE", None)
+        out["module_through_mgp_abi"] = {"scale": ms, "seconds": dt, "edges_per_s": mm * ITERATIONS / dt, "rows": int(len(nodes)),
+                                         "seconds_with_graph_cache_hit": dtc, "rank_sum_check": float(np.sum(ranks)),
+                                         "note": "CALL pagerank.get(20, 0.85, 0.0, 1) through libmgp_fake_host.so: pull "
+                                                 "(3 ABI calls per edge), upload, build, iterate, emit (5 ABI calls per row)"}
+    except Exception as ex:  # pragma: no cover
+        out["module_through_mgp_abi"] = {"unavailable": repr(ex)}
+    return out
+
+
 CLASS_NAMES = ["zero_rows", "sell_rows", "sell_epilogue_push", "heavy_segments", "heavy_finish", "iter_end_barrier"]
 
 
@@ -400,6 +486,17 @@ def run_b200_arm(args):
                "api": "mgb200_pagerank_run_partition(graph, params, host_rank_out, host_vertex_out) on every rank",
                "rank_sum_check": float(sm.item())}
 
+    # e2e_call: what ONE `CALL pagerank.get()` pays beyond the iteration -- host COO in, host ranks out, graph built inside
+    # the call.  (a) the one-shot C-ABI entry points at the benchmark scale, uint64 pairs as in the
+    # reference's EdgePair and uint32 dense ids as the module holds them; (b) the drop-in module through the mgp ABI
+    # (tests' fake host; ABI-bound: 3 calls per edge, 5 per emitted row) on a smaller graph.
+    e2e_call = None
+    if world == 1 and not args.no_e2e_call and lone <= 1:
+        try:
+            e2e_call = measure_e2e_call(args, mg, N, lib, device, scale, n, m, host_out)
+        except Exception as ex:  # pragma: no cover
+            log("e2e_call failed:", repr(ex))
+
     # N > 1: rank parity against the single-GPU result on the same graph, outside the timed region.  Every rank drops
     # its (vertex, rank) slice into a full-length vector (disjoint slices, summed over NVLink), rank 0 rebuilds the
     # WHOLE graph as one partition on its own GPU, runs the same call and compares all N ranks.
@@ -485,7 +582,7 @@ def run_b200_arm(args):
                    "heavy_rows": info["heavy_rows"], "heavy_edges": info["heavy_edges"], "sell_rows": info["sell_rows"],
                    "sell_entries": info["sell_entries"], "zero_rows": info["zero_rows"]},
         "ms_per_iteration": total_ms / args.steps / ITERATIONS,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "gpu_launches": launches, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_call": e2e_call, "parity": parity, "gpu_launches": launches, "clocks": clocks,
         "kernel_ms_per_iteration": {k: float(v) / (args.steps * ITERATIONS) for k, v in zip(CLASS_NAMES, class_ms)},
     }
     emit(line)
@@ -516,22 +613,132 @@ def run_bfs_arm(args):
     sources = [0] + [int(x) for x in rng.integers(0, n, size=max(args.steps + args.warmup, 1))]
     for s in sources[:max(args.warmup, 3)]:
         g.distances(s)
-    ms, reached, inspected, launches = [], [], [], 0
+    ms, reached, inspected, level_counts, launches = [], [], [], [], 0
     t0 = time.perf_counter()
     for s in sources[:args.steps]:
         dist, st = g.distances(s)
         ms.append(st["traverse_ms"]); reached.append(st["reached"]); inspected.append(st["edges_inspected"])
+        level_counts.append(st["levels"])
         launches += st["kernel_launches"]
     e2e_dt = time.perf_counter() - t0
     total = float(sum(ms))
+    # Roofline (HBM-bound integer work).  Algorithmic bytes of one direction-optimising traversal:
+    #   4 B per inspected adjacency entry + 12 B per reached vertex (8 B row offsets, 4 B distance written)
+    #   + 2 * N/8 B per level (frontier bitmap written, then read by the next level)
+    algo = [4 * i + 12 * r + 2 * (n // 8) * l for i, r, l in zip(inspected, reached, level_counts)]
+    peak, peak_src = hbm_peak()
+    achieved = float(sum(algo)) / (total * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "bfs traversal (all level kernels of one source)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_launch": float(np.mean(algo)),
+                "formula": "4*edges_inspected + 12*reached + 2*(N/8)*levels per traversal",
+                "note": "a traversal that inspects 4 % of the adjacency is latency-bound by its ~7 dependent levels, "
+                        "not by bytes; the fraction is reported for completeness"}
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(REPO, "tests"))
+            from _checkers import BfsOracle, oracle_rmat_edges  # bench.py's cpu_baseline leg may execute oracle/
+            cs = min(scale, 22)
+            cn, cm = 1 << cs, EDGE_FACTOR << cs
+            f, t = oracle_rmat_edges(cs, cm, seed=SEED)
+            t0 = time.perf_counter()
+            BfsOracle().distances(cn, f, t, 0)
+            dt = time.perf_counter() - t0
+            cpu = {"value": cm / dt, "unit": "edges/s", "cores": 1, "kind": "port",
+                   "sample": f"oracle/bfs_oracle.c (restatement of the cursor in src/query/plan/operator.cpp:2692-2912; the "
+                             f"engine cannot be built here), RMAT scale-{cs}, source 0, one traversal incl. adjacency build"}
+        except Exception as ex:
+            log("cpu_baseline failed:", ex)
     emit({"metric": "bfs_input_edges_per_second", "value": m * args.steps / (total * 1e-3), "unit": "edges/s",
           "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total / args.steps,
           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
           "config": {"workload": f"BFS expand (direction OUT, default bounds) RMAT scale-{scale} EF16 (N={n}, E={m}), "
                                  f"{args.steps} seeded sources", "graph_build_s": build_s,
-                     "reached_per_source": reached, "edges_inspected_per_source": inspected},
+                     "reached_per_source": reached, "edges_inspected_per_source": inspected, "levels_per_source": level_counts},
+          "roofline": roofline, "cpu_baseline": cpu,
           "e2e": {"value": m * args.steps / e2e_dt, "unit": "edges/s", "h2d_bytes_per_step": 32,
                   "d2h_bytes_per_step": 4 * n, "api": "mgb200_bfs_run(graph, source, ..., host_dist_out)"},
+          "gpu_launches": launches})
+    return 0
+
+
+def run_katz_arm(args):
+    """Next path (SURVEY 8f-1): static Katz centrality, katz_alg::SetKatz, on RMAT scale-22 (1 GPU).  A step is one
+    SetKatz call on the device-resident graph; value = E * iterations / loop time (CUDA events)."""
+    import memgraph_b200 as mg
+    from memgraph_b200 import _native as N
+    from memgraph_b200 import katz as K
+    lib = N.lib()
+    scale = args.scale if args.scale != 26 else 22
+    n, m = 1 << scale, EDGE_FACTOR << scale
+    d_from = dev_alloc(N, lib, 0, 4 * m)
+    d_to = dev_alloc(N, lib, 0, 4 * m)
+    mg.rmat_edges_device(scale, m, d_from, d_to, seed=SEED, device=0)
+    g = mg.PageRankGraph.from_device(n, m, d_from, d_to)
+    lib.mgb200_device_free(0, d_from)
+    lib.mgb200_device_free(0, d_to)
+    # alpha: the module's default 0.2 makes gamma negative on a skewed graph (alpha^2 deg_max > 1) and the reference stops
+    # after ONE iteration; the benchmark uses the largest "real" problem, alpha = 0.9 / sqrt(deg_max + 1), epsilon = 1e-3
+    try:
+        _, st0 = K.set_katz(g, 0.2, 1e-2, 1)
+    except K.NotConverged as ex:
+        st0 = ex.stats
+    deg_max = st0["max_out_degree"]
+    alpha, eps = 0.9 / float(np.sqrt(deg_max + 1.0)), 1e-3
+    for _ in range(max(args.warmup, 3)):
+        K.set_katz(g, alpha, eps)
+    ms, iters, launches = [], 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cent, st = K.set_katz(g, alpha, eps)
+        ms.append(st["iterate_ms"]); iters = st["iterations"]; launches += st["kernel_launches"]
+    e2e_dt = time.perf_counter() - t0
+    total = float(sum(ms))
+    info = g.info
+    g.close()
+    # per iteration: the gather phase (12 B per edge like PageRank) + per vertex: omega written 8, c read+written 16, ur
+    # written 8, row offset 4 = 36 B, + the separation test reading c, ur once and writing/reading one sort key = 24 B
+    algo_iter = 12 * m + 60 * n
+    peak, peak_src = hbm_peak()
+    achieved = algo_iter * iters * args.steps / (total * 1e-3) / 1e9
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(REPO, "tests"))
+            from _checkers import oracle_rmat_edges
+            from test_katz_oracle import oracle_katz, ref_katz, KATZ_REF_SO
+            cs = min(scale, 20)
+            cn, cm = 1 << cs, EDGE_FACTOR << cs
+            f, t = oracle_rmat_edges(cs, cm, seed=SEED)
+            dmax = int(np.bincount(f.astype(np.int64), minlength=cn).max())
+            ca = 0.9 / float(np.sqrt(dmax + 1.0))
+            rc, _c, cit = oracle_katz(cn, f, t, ca, eps)
+            kind = "reference" if os.path.exists(KATZ_REF_SO) else "port"
+            t0 = time.perf_counter()
+            if kind == "reference":
+                ref_katz(cn, f, t, ca, eps)
+            else:
+                oracle_katz(cn, f, t, ca, eps)
+            dt = time.perf_counter() - t0
+            cpu = {"value": cm * cit / dt, "unit": "edges/s", "cores": 1, "kind": kind,
+                   "sample": f"katz_alg::SetKatz on RMAT scale-{cs}, alpha {ca:.4g}, epsilon {eps}, {cit} iterations, graph "
+                             f"ingest included (the reference builds its adjacency inside the call)"}
+        except Exception as ex:
+            log("cpu_baseline failed:", ex)
+    emit({"metric": "katz_edges_per_second", "value": m * iters * args.steps / (total * 1e-3), "unit": "edges/s", "n_gpus": 1,
+          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total / args.steps, "higher_is_better": True,
+          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+          "config": {"workload": f"Katz centrality (SetKatz) RMAT scale-{scale} EF16 (N={n}, E={m}), alpha {alpha:.5g} "
+                                 f"(= 0.9/sqrt(deg_max+1), deg_max {deg_max}), epsilon {eps}, {iters} iterations to separation",
+                     "heavy_rows": info["heavy_rows"], "sell_rows": info["sell_rows"], "zero_rows": info["zero_rows"]},
+          "ms_per_iteration": total / args.steps / max(iters, 1),
+          "roofline": {"bound": "hbm", "kernel": "whole Katz iteration (gather kernels + epilogue + separation test)",
+                       "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                       "traffic": None, "algorithmic_bytes_per_launch": algo_iter, "formula": "12*E + 60*N per iteration"},
+          "cpu_baseline": cpu,
+          "e2e": {"value": m * iters * args.steps / e2e_dt, "unit": "edges/s", "h2d_bytes_per_step": 24,
+                  "d2h_bytes_per_step": 8 * n, "api": "mgb200_katz_run(graph, alpha, epsilon, 0, host_centrality_out)"},
           "gpu_launches": launches})
     return 0
 
@@ -546,9 +753,10 @@ def main():
     ap.add_argument("--cpu-scale", type=int, default=int(os.environ.get("MGB200_CPU_SCALE", "24")),
                     help="RMAT scale of the bounded CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e-call", action="store_true", help="skip the one-shot host-COO-in / host-ranks-out measurement")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the comparison with the single-GPU result")
-    ap.add_argument("--workload", default="pagerank", choices=["pagerank", "bfs"],
-                    help="pagerank (the BASELINE metric, default) or bfs (the next path, config #5)")
+    ap.add_argument("--workload", default="pagerank", choices=["pagerank", "bfs", "katz"],
+                    help="pagerank (the BASELINE metric, default), bfs (config #5) or katz (SURVEY 8f-1)")
     ap.add_argument("--quick", action="store_true", help="sweep mode: device-resident timing only, compact JSON")
     args = ap.parse_args()
     global REAL_STDOUT
@@ -559,6 +767,8 @@ def main():
         return run_reference_arm(args)
     if args.workload == "bfs":
         return run_bfs_arm(args)
+    if args.workload == "katz":
+        return run_katz_arm(args)
     return run_b200_arm(args)
 
 

@@ -63,6 +63,7 @@ typedef struct mgb200_graph_info {
   uint64_t zero_rows;      /* in-degree 0: rank is the constant (1-d)/N after iter 1  */
   uint64_t resident_bytes; /* device bytes held by the handle after build             */
   double build_ms;         /* device time of the CSR/SELL build                       */
+  double upload_ms;        /* host COO -> device, wall clock (0 for create_device)    */
 } mgb200_graph_info;
 
 typedef struct mgb200_run_stats {
@@ -105,6 +106,18 @@ int mgb200_device_count(int *count_out);
 int mgb200_graph_create_host(int device, uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
                              uint32_t part_rank, uint32_t part_world, mgb200_graph **out);
 
+/* Same for callers that hold 32-bit dense ids already (the query module narrows while it pulls the graph through
+ * the mgp iterators): half the host memory, nothing to narrow.  Both host forms stage through pinned, double-buffered
+ * chunks filled by a few host threads (MGB200_INGEST_THREADS, default min(16, cores/2)) while the previous chunk is
+ * on the wire: one pass, 8 bytes per edge over PCIe. */
+int mgb200_graph_create_host_u32(int device, uint64_t n, uint64_t m, const uint32_t *from, const uint32_t *to,
+                                 uint32_t part_rank, uint32_t part_world, mgb200_graph **out);
+
+/* Host-only: 128-bit order-sensitive fingerprint of a dense COO.  The mgp ABI has no graph version, so a module that
+ * wants to keep the device graph across CALLs (MGB200_GRAPH_CACHE=1 in pagerank.so) compares fingerprints of what it
+ * pulled.  The value depends on MGB200_INGEST_THREADS (the partial hashes are combined per thread). */
+int mgb200_coo_fingerprint_u32(uint64_t n, uint64_t m, const uint32_t *from, const uint32_t *to, uint64_t out[2]);
+
 /* Same, COO already resident on `device` as uint32 (the inputs are read, not consumed). */
 int mgb200_graph_create_device(int device, uint64_t n, uint64_t m, const uint32_t *d_from, const uint32_t *d_to,
                                uint32_t part_rank, uint32_t part_world, mgb200_graph **out);
@@ -140,6 +153,10 @@ int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint6
 int mgb200_pagerank_multi(uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
                           const mgb200_run_params *params, uint32_t number_of_threads, uint32_t gpu_count,
                           const int *devices, double *rank_out, uint64_t *iterations_out);
+
+int mgb200_pagerank_multi_u32(uint64_t n, uint64_t m, const uint32_t *from, const uint32_t *to,
+                              const mgb200_run_params *params, uint32_t number_of_threads, uint32_t gpu_count,
+                              const int *devices, double *rank_out, uint64_t *iterations_out);
 
 /* ---- multi-GPU: one partition per GPU, contributions pushed to peers over NVLink --------------- */
 

@@ -17,7 +17,7 @@ class GraphInfo(ctypes.Structure):
     _fields_ = [("node_count", u64), ("edge_count", u64), ("part_rank", u32), ("part_world", u32),
                 ("local_rows", u64), ("local_edges", u64), ("heavy_rows", u64), ("heavy_edges", u64),
                 ("heavy_segments", u64), ("sell_rows", u64), ("sell_slices", u64), ("sell_entries", u64),
-                ("zero_rows", u64), ("resident_bytes", u64), ("build_ms", f64)]
+                ("zero_rows", u64), ("resident_bytes", u64), ("build_ms", f64), ("upload_ms", f64)]
 
 
 class RunStatsC(ctypes.Structure):
@@ -49,6 +49,8 @@ EXPORTS = {
     "mgb200_last_error": (ctypes.c_char_p, []),
     "mgb200_device_count": (i32, [ctypes.POINTER(i32)]),
     "mgb200_graph_create_host": (i32, [i32, u64, u64, vp, vp, u32, u32, ctypes.POINTER(vp)]),
+    "mgb200_graph_create_host_u32": (i32, [i32, u64, u64, vp, vp, u32, u32, ctypes.POINTER(vp)]),
+    "mgb200_coo_fingerprint_u32": (i32, [u64, u64, vp, vp, vp]),
     "mgb200_graph_create_device": (i32, [i32, u64, u64, vp, vp, u32, u32, ctypes.POINTER(vp)]),
     "mgb200_graph_destroy": (None, [vp]),
     "mgb200_graph_get_info": (i32, [vp, ctypes.POINTER(GraphInfo)]),
@@ -57,6 +59,7 @@ EXPORTS = {
     "mgb200_parallel_iterative_pagerank_multi": (i32, [u64, u64, vp, vp, u64, f64, f64, u32, u32, vp, vp,
                                                        ctypes.POINTER(u64)]),
     "mgb200_pagerank_multi": (i32, [u64, u64, vp, vp, ctypes.POINTER(RunParams), u32, u32, vp, vp, ctypes.POINTER(u64)]),
+    "mgb200_pagerank_multi_u32": (i32, [u64, u64, vp, vp, ctypes.POINTER(RunParams), u32, u32, vp, vp, ctypes.POINTER(u64)]),
     "mgb200_partition_range": (i32, [u64, u32, u32, ctypes.POINTER(u64), ctypes.POINTER(u64)]),
     "mgb200_partition_locate": (i32, [u64, u64, u32, i32, u64, ctypes.POINTER(u32), ctypes.POINTER(u64)]),
     "mgb200_partition_label": (i32, [u64, u64, u32, i32, u32, u64, ctypes.POINTER(u64), ctypes.POINTER(u64)]),

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -235,8 +236,111 @@ int mgb200_graph_create_device(int device, uint64_t n, uint64_t m, const uint32_
   return MGB200_OK;
 }
 
-int mgb200_graph_create_host(int device, uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
-                             uint32_t part_rank, uint32_t part_world, mgb200_graph **out) {
+}  // extern "C"
+
+namespace {
+
+// ---- host COO -> device uint32 COO: pinned, double-buffered, single pass ------------------------------------------
+// The reference's ingest ends in host vectors (pagerank_module.cpp:18-54); this is the hop from there to the device.
+// r01 staged pageable uint64 chunks synchronously, twice (16 B per edge over PCIe at the driver's single-threaded
+// pageable rate).  Now a few host threads narrow (or copy) chunk c into pinned buffer c & 1 -- validating the
+// endpoints on the way -- while the copy engine ships buffer (c - 1) & 1: 8 B per edge on the link, both endpoints
+// of an edge in the same pass.  The pinned staging (4 x 64 MiB) is kept for the life of the process: allocating it
+// costs more than the upload of a small graph.
+constexpr uint64_t kIngestChunk = 1ull << 24;  // edges per staging buffer
+
+struct IngestStaging {
+  std::mutex busy;
+  uint32_t *pinned[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [buffer][from / to]
+  cudaEvent_t shipped[2] = {nullptr, nullptr};
+  cudaStream_t stream = nullptr;
+  int device = -1;
+  int ensure(int dev) {
+    if (device == dev && pinned[0][0]) return MGB200_OK;
+    release();
+    MGB_CUDA(cudaSetDevice(dev));
+    for (auto &buf : pinned)
+      for (auto &p : buf) MGB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&p), kIngestChunk * sizeof(uint32_t), cudaHostAllocDefault));
+    for (auto &e : shipped) MGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    MGB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    device = dev;
+    return MGB200_OK;
+  }
+  void release() {
+    for (auto &buf : pinned)
+      for (auto &p : buf) {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+      }
+    for (auto &e : shipped) {
+      if (e) cudaEventDestroy(e);
+      e = nullptr;
+    }
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+    device = -1;
+  }
+};
+IngestStaging g_staging;  // one upload at a time per process; a second concurrent caller allocates its own
+
+unsigned ingest_threads() {
+  const char *s = getenv("MGB200_INGEST_THREADS");
+  if (s && atoi(s) > 0) return static_cast<unsigned>(std::min(atoi(s), 64));
+  const unsigned hw = std::thread::hardware_concurrency();
+  return std::max(1u, std::min(16u, hw / 2));
+}
+
+template <typename T>
+int upload_coo(int device, uint64_t n, uint64_t m, const T *from, const T *to, uint32_t *d_from, uint32_t *d_to) {
+  std::unique_lock<std::mutex> lock(g_staging.busy, std::try_to_lock);
+  IngestStaging local;
+  IngestStaging &st = lock.owns_lock() ? g_staging : local;
+  int rc = st.ensure(device);
+  if (rc) return rc;
+  const unsigned threads = ingest_threads();
+  std::atomic<int> bad{0};
+  for (uint64_t off = 0, c = 0; off < m; off += kIngestChunk, ++c) {
+    const uint64_t cnt = std::min(kIngestChunk, m - off);
+    const int b = static_cast<int>(c & 1);
+    if (c >= 2) MGB_CUDA(cudaEventSynchronize(st.shipped[b]));  // the copy that last read this buffer is done
+    auto work = [&, b, off, cnt](unsigned t, unsigned nt) {
+      const uint64_t lo = cnt * t / nt, hi = cnt * (t + 1) / nt;
+      uint32_t *pf = st.pinned[b][0], *pt = st.pinned[b][1];
+      T worst = 0;
+      for (uint64_t i = lo; i < hi; ++i) {
+        const T f = from[off + i], d = to[off + i];
+        worst = std::max(worst, std::max(f, d));
+        pf[i] = static_cast<uint32_t>(f);
+        pt[i] = static_cast<uint32_t>(d);
+      }
+      if (static_cast<uint64_t>(worst) >= n) bad.store(1, std::memory_order_relaxed);
+    };
+    const unsigned nt = cnt < (1u << 16) ? 1u : threads;
+    if (nt == 1) {
+      work(0, 1);
+    } else {
+      std::vector<std::thread> pool;
+      for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t, nt);
+      work(0, nt);
+      for (auto &th : pool) th.join();
+    }
+    if (bad.load(std::memory_order_relaxed)) break;
+    MGB_CUDA(cudaMemcpyAsync(d_from + off, st.pinned[b][0], cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, st.stream));
+    MGB_CUDA(cudaMemcpyAsync(d_to + off, st.pinned[b][1], cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, st.stream));
+    MGB_CUDA(cudaEventRecord(st.shipped[b], st.stream));
+  }
+  MGB_CUDA(cudaStreamSynchronize(st.stream));
+  if (!lock.owns_lock()) local.release();
+  if (bad.load()) {
+    set_error("edge endpoint out of range (>= number_of_nodes)");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  return MGB200_OK;
+}
+
+template <typename T>
+int create_from_host(int device, uint64_t n, uint64_t m, const T *from, const T *to, uint32_t part_rank,
+                     uint32_t part_world, mgb200_graph **out) {
   if (!out) return MGB200_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   if (m > 0 && (!from || !to)) {
@@ -248,56 +352,68 @@ int mgb200_graph_create_host(int device, uint64_t n, uint64_t m, const uint64_t 
   rc = check_device(device);
   if (rc) return rc;
   MGB_CUDA(cudaSetDevice(device));
-  // Stage the uint64 COO in chunks and narrow it to uint32 on the device.
   uint32_t *d_from = nullptr, *d_to = nullptr;
-  uint64_t *d_stage = nullptr;
-  int *d_bad = nullptr;
-  const uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(m, 1), 1ull << 26);
-  auto cleanup = [&]() {
-    cudaFree(d_from);
-    cudaFree(d_to);
-    cudaFree(d_stage);
-    cudaFree(d_bad);
-  };
   cudaError_t e;
   if ((e = cudaMalloc(&d_from, std::max<uint64_t>(m, 1) * sizeof(uint32_t))) != cudaSuccess ||
-      (e = cudaMalloc(&d_to, std::max<uint64_t>(m, 1) * sizeof(uint32_t))) != cudaSuccess ||
-      (e = cudaMalloc(&d_stage, chunk * sizeof(uint64_t))) != cudaSuccess ||
-      (e = cudaMalloc(&d_bad, sizeof(int))) != cudaSuccess || (e = cudaMemset(d_bad, 0, sizeof(int))) != cudaSuccess) {
-    cleanup();
-    return cuda_fail(e, "cudaMalloc(COO staging)", __FILE__, __LINE__);
+      (e = cudaMalloc(&d_to, std::max<uint64_t>(m, 1) * sizeof(uint32_t))) != cudaSuccess) {
+    cudaFree(d_from);
+    return cuda_fail(e, "cudaMalloc(COO)", __FILE__, __LINE__);
   }
-  for (int side = 0; side < 2; ++side) {
-    const uint64_t *src = side == 0 ? from : to;
-    uint32_t *dst = side == 0 ? d_from : d_to;
-    for (uint64_t off = 0; off < m; off += chunk) {
-      const uint64_t cnt = std::min(chunk, m - off);
-      if ((e = cudaMemcpy(d_stage, src + off, cnt * sizeof(uint64_t), cudaMemcpyHostToDevice)) != cudaSuccess) {
-        cleanup();
-        return cuda_fail(e, "cudaMemcpy(COO H2D)", __FILE__, __LINE__);
-      }
-      rc = narrow_edges_u64_to_u32(device, nullptr, n, cnt, d_stage, dst + off, d_bad);
-      if (rc) {
-        cleanup();
-        return rc;
-      }
-    }
-  }
-  int bad = 0;
-  if ((e = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) {
-    cleanup();
-    return cuda_fail(e, "cudaMemcpy(flag)", __FILE__, __LINE__);
-  }
-  if (bad) {
-    cleanup();
-    set_error("edge endpoint out of range (>= number_of_nodes)");
-    return MGB200_ERR_INVALID_ARGUMENT;
-  }
-  cudaFree(d_stage);
-  d_stage = nullptr;
-  rc = mgb200_graph_create_device(device, n, m, d_from, d_to, part_rank, part_world, out);
-  cleanup();
+  const auto t0 = std::chrono::steady_clock::now();
+  rc = upload_coo(device, n, m, from, to, d_from, d_to);
+  const double upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (!rc) rc = mgb200_graph_create_device(device, n, m, d_from, d_to, part_rank, part_world, out);
+  cudaFree(d_from);
+  cudaFree(d_to);
+  if (!rc) (*out)->g.upload_ms = upload_ms;
   return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgb200_graph_create_host(int device, uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
+                             uint32_t part_rank, uint32_t part_world, mgb200_graph **out) {
+  return create_from_host(device, n, m, from, to, part_rank, part_world, out);
+}
+
+int mgb200_graph_create_host_u32(int device, uint64_t n, uint64_t m, const uint32_t *from, const uint32_t *to,
+                                 uint32_t part_rank, uint32_t part_world, mgb200_graph **out) {
+  return create_from_host(device, n, m, from, to, part_rank, part_world, out);
+}
+
+// 128-bit fingerprint of a dense COO (order-sensitive), for callers that keep a device graph across calls and need to
+// know whether the graph they just pulled is the one already resident (the mgp ABI carries no graph version).
+int mgb200_coo_fingerprint_u32(uint64_t n, uint64_t m, const uint32_t *from, const uint32_t *to, uint64_t out[2]) {
+  if (!out || (m > 0 && (!from || !to))) return MGB200_ERR_INVALID_ARGUMENT;
+  const unsigned threads = m < (1u << 18) ? 1u : ingest_threads();
+  std::vector<uint64_t> part(static_cast<size_t>(threads) * 2, 0);
+  auto work = [&](unsigned t) {
+    const uint64_t lo = m * t / threads, hi = m * (t + 1) / threads;
+    uint64_t a = 0x9E3779B97F4A7C15ull ^ lo, b = 0xC2B2AE3D27D4EB4Full ^ hi;
+    for (uint64_t i = lo; i < hi; ++i) {
+      const uint64_t v = (static_cast<uint64_t>(from[i]) << 32) | to[i];
+      a = (a ^ v) * 0xBF58476D1CE4E5B9ull;
+      a ^= a >> 29;
+      b = (b + v) * 0x94D049BB133111EBull;
+      b ^= b >> 31;
+    }
+    part[2 * t] = a;
+    part[2 * t + 1] = b;
+  };
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < threads; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto &th : pool) th.join();
+  uint64_t a = n * 0xD6E8FEB86659FD93ull + m, b = m ^ 0xA24BAED4963EE407ull;
+  for (unsigned t = 0; t < threads; ++t) {  // fixed combination order; the thread count is part of the definition
+    a = (a ^ part[2 * t]) * 0xBF58476D1CE4E5B9ull + t;
+    b = (b + part[2 * t + 1]) * 0x94D049BB133111EBull + threads;
+  }
+  out[0] = a;
+  out[1] = b;
+  return MGB200_OK;
 }
 
 void mgb200_graph_destroy(mgb200_graph *g) {
@@ -324,6 +440,7 @@ int mgb200_graph_get_info(const mgb200_graph *h, mgb200_graph_info *info) {
   info->zero_rows = g.n_zero;
   info->resident_bytes = g.resident_bytes;
   info->build_ms = g.build_ms;
+  info->upload_ms = g.upload_ms;
   return MGB200_OK;
 }
 
@@ -435,13 +552,15 @@ int mgb200_parallel_iterative_pagerank(uint64_t n, uint64_t m, const uint64_t *f
   return MGB200_OK;
 }
 
+}  // extern "C"
+
 namespace {
 int poll_flag(void *user) { return static_cast<std::atomic<int> *>(user)->load(std::memory_order_relaxed); }
-}  // namespace
 
-int mgb200_pagerank_multi(uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
-                          const mgb200_run_params *params, uint32_t number_of_threads, uint32_t gpu_count,
-                          const int *devices, double *rank_out, uint64_t *iterations_out) {
+template <typename T>
+int pagerank_multi_impl(uint64_t n, uint64_t m, const T *from, const T *to, const mgb200_run_params *params,
+                        uint32_t number_of_threads, uint32_t gpu_count, const int *devices, double *rank_out,
+                        uint64_t *iterations_out) {
   if (!params) return MGB200_ERR_INVALID_ARGUMENT;
   if (params->rank_out_on_device) {
     set_error("mgb200_pagerank_multi gathers into host memory (rank_out_on_device must be 0)");
@@ -457,12 +576,12 @@ int mgb200_pagerank_multi(uint64_t n, uint64_t m, const uint64_t *from, const ui
   }
   if (gpu_count <= 1 || n == 0) {
     if (n == 0)
-      return mgb200_parallel_iterative_pagerank(n, m, from, to, params->max_iterations, params->damping_factor,
+      return mgb200_parallel_iterative_pagerank(n, 0, nullptr, nullptr, params->max_iterations, params->damping_factor,
                                                 params->stop_epsilon, number_of_threads, rank_out, iterations_out);
     const char *dev_env = getenv("MGB200_DEVICE");
     const int device = devices ? devices[0] : (dev_env ? atoi(dev_env) : 0);
     mgb200_graph *g = nullptr;
-    int rc = mgb200_graph_create_host(device, n, m, from, to, 0, 1, &g);
+    int rc = create_from_host(device, n, m, from, to, 0, 1, &g);
     if (rc) return rc;
     mgb200_run_stats stats{};
     rc = mgb200_pagerank_run(g, params, rank_out, &stats);
@@ -476,7 +595,7 @@ int mgb200_pagerank_multi(uint64_t n, uint64_t m, const uint64_t *from, const ui
   };
   for (uint32_t q = 0; q < gpu_count; ++q) {
     const int dev = devices ? devices[q] : static_cast<int>(q);
-    const int rc = mgb200_graph_create_host(dev, n, m, from, to, q, gpu_count, &parts[q]);
+    const int rc = create_from_host(dev, n, m, from, to, q, gpu_count, &parts[q]);
     if (rc) {
       destroy_all();
       return rc;
@@ -532,6 +651,22 @@ int mgb200_pagerank_multi(uint64_t n, uint64_t m, const uint64_t *from, const ui
     for (size_t r = 0; r < ranks[q].size(); ++r) rank_out[vertices[q][r]] = ranks[q][r];
   if (iterations_out) *iterations_out = stats[0].iterations;
   return MGB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgb200_pagerank_multi(uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,
+                          const mgb200_run_params *params, uint32_t number_of_threads, uint32_t gpu_count,
+                          const int *devices, double *rank_out, uint64_t *iterations_out) {
+  return pagerank_multi_impl(n, m, from, to, params, number_of_threads, gpu_count, devices, rank_out, iterations_out);
+}
+
+int mgb200_pagerank_multi_u32(uint64_t n, uint64_t m, const uint32_t *from, const uint32_t *to,
+                              const mgb200_run_params *params, uint32_t number_of_threads, uint32_t gpu_count,
+                              const int *devices, double *rank_out, uint64_t *iterations_out) {
+  return pagerank_multi_impl(n, m, from, to, params, number_of_threads, gpu_count, devices, rank_out, iterations_out);
 }
 
 int mgb200_parallel_iterative_pagerank_multi(uint64_t n, uint64_t m, const uint64_t *from, const uint64_t *to,

@@ -206,6 +206,7 @@ struct Graph {
 
   uint64_t resident_bytes = 0;
   double build_ms = 0.0;
+  double upload_ms = 0.0;  // host COO -> device (mgb200_graph_create_host*), wall clock
   cudaEvent_t ev[4] = {};
   // side stream for the SELL epilogue (overlaps the peer push with the heavy-row kernels)
   cudaStream_t stream2 = nullptr;
@@ -224,6 +225,7 @@ struct Graph {
     bool multi_aware = true;     // MGB200_MULTI_AWARE=0: legacy "global label prefix is hot" on every partition
     bool force_multi_path = false;  // MGB200_FORCE_MULTI_PATH=1: run the multi-partition gather code on one GPU (measurement)
     bool stream_kernel = false;  // MGB200_SELL_KERNEL=stream
+    int push_ctas = 1;           // MGB200_PUSH_CTAS: CTAs per SM of the SELL epilogue + peer push on several partitions (0 = full grid)
     int sell_mode = -1;          // MGB200_SELL_MODE: 0 ticket queue, 1 static deal, -1 (default) by partition size
     bool global_order = false;   // MGB200_LABELLING=global: label = global degree order, blocks of 32 dealt (RowMap)
     bool push_mask = false;      // MGB200_PUSH_MASK=1: push a contribution only to the partitions that gather it

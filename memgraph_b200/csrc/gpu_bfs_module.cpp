@@ -67,19 +67,17 @@ void Distances(mgp_list *args, mgp_graph *graph, mgp_result *result, mgp_memory 
     mgp_vertex_id source_id{};
     Check(mgp_vertex_get_id(source, &source_id));
 
-    const HostGraph hg = PullGraph(graph, memory);
+    // an edge to a vertex the iterator never showed is dropped here: the reference cursor has no "map it to the first
+    // vertex" behaviour (that is a PageRank-module quirk), and a fabricated edge would change distances
+    const HostGraph hg = PullGraph(graph, memory, UnknownGid::kUnknownDropped);
     const uint64_t n = hg.gid_of_dense.size();
     uint64_t source_dense = n;
-    for (uint64_t v = 0; v < n; ++v)
-      if (hg.gid_of_dense[v] == source_id.as_int) {
-        source_dense = v;
-        break;
-      }
-    if (source_dense == n) throw ModuleError("Invalid ID!");
+    if (!hg.dense_of_gid.Find(source_id.as_int, &source_dense)) throw ModuleError("Invalid ID!");
 
     const char *dev_env = std::getenv("MGB200_DEVICE");
     mgb200_bfs_graph *dg = nullptr;
-    if (mgb200_bfs_graph_create_host(dev_env ? std::atoi(dev_env) : 0, n, hg.from.size(), hg.from.data(), hg.to.data(),
+    const std::vector<uint64_t> from64(hg.from.begin(), hg.from.end()), to64(hg.to.begin(), hg.to.end());
+    if (mgb200_bfs_graph_create_host(dev_env ? std::atoi(dev_env) : 0, n, from64.size(), from64.data(), to64.data(),
                                      &dg) != MGB200_OK)
       throw ModuleError(mgb200_last_error());
     std::vector<int32_t> dist(n);

@@ -342,6 +342,11 @@ uint32_t env_u32(const char *name, uint32_t fallback) {
   return v ? static_cast<uint32_t>(v) : fallback;
 }
 
+uint32_t env_u32_zero(const char *name, uint32_t fallback) {  // like env_u32, but "0" is a value
+  const char *s = getenv(name);
+  return (s && *s) ? static_cast<uint32_t>(strtoul(s, nullptr, 10)) : fallback;
+}
+
 int bits_for(uint64_t v) {  // number of bits needed to represent values < v
   int b = 0;
   while (b < 64 && (v >> b) != 0) ++b;
@@ -399,7 +404,12 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   MGB_CUDA(cudaGetDeviceProperties(&prop, g.device));
   g.sm_count = prop.multiProcessorCount;
   MGB_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-  MGB_CUDA(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
+  {  // the side stream carries the SELL epilogue + peer push: highest priority, so that its few CTAs are placed before
+     // the heavy-row kernel's when both become ready at the end of the SELL kernel
+    int prio_low = 0, prio_high = 0;
+    MGB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+    MGB_CUDA(cudaStreamCreateWithPriority(&g.stream2, cudaStreamNonBlocking, prio_high));
+  }
   MGB_CUDA(cudaEventCreateWithFlags(&g.fork_ev, cudaEventDisableTiming));
   MGB_CUDA(cudaEventCreateWithFlags(&g.join_ev, cudaEventDisableTiming));
   MGB_CUDA(cudaEventCreateWithFlags(&g.sell_ready_ev, cudaEventDisableTiming));
@@ -414,6 +424,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     if ((s = getenv("MGB200_SELL_KERNEL")) != nullptr) g.tun.stream_kernel = strcmp(s, "stream") == 0;
     if ((s = getenv("MGB200_IDX_FLAGS")) != nullptr) g.tun.idx_flags = atoi(s);
     if ((s = getenv("MGB200_SELL_MODE")) != nullptr) g.tun.sell_mode = atoi(s);
+    if ((s = getenv("MGB200_PUSH_CTAS")) != nullptr) g.tun.push_ctas = std::max(0, atoi(s));
     if ((s = getenv("MGB200_LABELLING")) != nullptr) g.tun.global_order = strcmp(s, "global") == 0;
     if ((s = getenv("MGB200_PUSH_MASK")) != nullptr) g.tun.push_mask = s[0] == '1';
     if ((s = getenv("MGB200_LONE_PARTITION")) != nullptr) g.tun.lone_partition = s[0] == '1';
@@ -719,7 +730,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     // queue over ~16 items per warp wins (whole graph 2.12 vs 2.51 ms), below that every extra run start costs more
     // than the balance gains and ONE (or two) contiguous runs per warp, dealt statically, are fastest
     // (1/8 partition: 0.37 vs 0.56 ms; 1/4: 0.68 vs 0.77 ms).
-    constexpr uint64_t kSliceCost = 8;
+    const uint64_t kSliceCost = env_u32_zero("MGB200_SLICE_COST", 8);
     const uint64_t resident_warps = static_cast<uint64_t>(g.sm_count) * 32u;  // 4 CTAs x 8 warps per SM
     const uint64_t per_warp = g.n_slices / resident_warps;
     g.sell_static = g.tun.sell_mode >= 0 ? g.tun.sell_mode == 1 : per_warp < 64;

@@ -117,6 +117,18 @@ class GidMap {
     if ((size_ + 1) * 2 > keys_.size()) Grow();
     Insert(gid, dense);
   }
+  bool Find(int64_t gid, uint64_t *dense) const {
+    if (keys_.empty()) return false;
+    std::size_t i = Hash(gid) & mask_;
+    while (vals_[i] != kEmpty) {
+      if (keys_[i] == gid) {
+        *dense = vals_[i];
+        return true;
+      }
+      i = (i + 1) & mask_;
+    }
+    return false;
+  }
   uint64_t GetOrZero(int64_t gid) const {
     if (keys_.empty()) return 0;
     std::size_t i = Hash(gid) & mask_;
@@ -168,14 +180,23 @@ class GidMap {
 
 struct HostGraph {
   std::vector<int64_t> gid_of_dense;  // reference id_to_memgraph (:42)
-  std::vector<uint64_t> from, to;     // dense (source, destination) per edge, in iteration order
+  std::vector<uint32_t> from, to;     // dense (source, destination) per edge, in iteration order; 32-bit: the device
+                                      // labels are, and the pull is the place to narrow (half the host memory, no
+                                      // second pass before the upload)
+  GidMap dense_of_gid;                // reference memgraph_to_id
 };
 
 inline bool MustAbort(mgp_graph *graph) { return mgp_must_abort != nullptr && mgp_must_abort(graph) != 0; }
 
+// What to do with an edge whose destination was never visited by the vertex iterator (possible in analytical mode):
+//   kUnknownToZero  the reference PageRank quirk, kept for drop-in fidelity: operator[] maps it to dense id 0 (:50)
+//   kUnknownDropped the edge is dropped -- for paths whose reference has no such quirk (BFS: a fabricated edge to the
+//                   first vertex would change distances)
+enum class UnknownGid { kUnknownToZero, kUnknownDropped };
+
 // The reference's ingest (CreatePageRankGraph :18-54): one vertex iterator, one out-edge iterator per
 // vertex, dense id = visit index, destinations remapped afterwards.
-inline HostGraph PullGraph(mgp_graph *graph, mgp_memory *memory) {
+inline HostGraph PullGraph(mgp_graph *graph, mgp_memory *memory, UnknownGid policy = UnknownGid::kUnknownToZero) {
   HostGraph hg;
   std::size_t approx_vertices = 0, approx_edges = 0;
   Check(mgp_graph_approximate_vertex_count(graph, &approx_vertices));
@@ -184,7 +205,7 @@ inline HostGraph PullGraph(mgp_graph *graph, mgp_memory *memory) {
   hg.from.reserve(approx_edges);
   std::vector<int64_t> to_gid;
   to_gid.reserve(approx_edges);
-  GidMap dense_of_gid;
+  GidMap &dense_of_gid = hg.dense_of_gid;
   dense_of_gid.Reserve(approx_vertices);
 
   VerticesIt vertices(graph, memory);
@@ -192,6 +213,7 @@ inline HostGraph PullGraph(mgp_graph *graph, mgp_memory *memory) {
     mgp_vertex_id source_id{};
     Check(mgp_vertex_get_id(source, &source_id));
     const uint64_t source_dense = hg.gid_of_dense.size();
+    if (source_dense >= 0xFFFFFFFEull) throw ModuleError("graph has more than 2^32 - 2 vertices");
     {
       OutEdgesIt edges(source, memory);
       for (mgp_edge *edge = edges.Get(); edge != nullptr; edge = edges.Next()) {
@@ -199,21 +221,29 @@ inline HostGraph PullGraph(mgp_graph *graph, mgp_memory *memory) {
         Check(mgp_edge_get_to(edge, &destination));
         mgp_vertex_id destination_id{};
         Check(mgp_vertex_get_id(destination, &destination_id));
-        hg.from.push_back(source_dense);
+        hg.from.push_back(static_cast<uint32_t>(source_dense));
         to_gid.push_back(destination_id.as_int);
       }
     }
     dense_of_gid.Put(source_id.as_int, source_dense);
     hg.gid_of_dense.push_back(source_id.as_int);
-    if ((source_dense & 0xFFF) == 0 && MustAbort(graph)) throw ModuleError("pagerank.get aborted by the host");
+    if ((source_dense & 0xFFF) == 0 && MustAbort(graph)) throw ModuleError("procedure aborted by the host");
   }
-  hg.to.resize(to_gid.size());
-  for (std::size_t e = 0; e < to_gid.size(); ++e) hg.to[e] = dense_of_gid.GetOrZero(to_gid[e]);
   // Reference quirk kept: `from` was recorded as the visit index, but the reference remaps the SOURCE
   // gid through the map as well (:50); the two differ only if a gid is visited twice, where the map
   // holds the later index.
-  for (std::size_t e = 0; e < hg.from.size(); ++e)
-    hg.from[e] = dense_of_gid.GetOrZero(hg.gid_of_dense[hg.from[e]]);
+  hg.to.resize(to_gid.size());
+  std::size_t kept = 0;
+  for (std::size_t e = 0; e < to_gid.size(); ++e) {
+    uint64_t dst = 0;
+    const bool known = dense_of_gid.Find(to_gid[e], &dst);
+    if (!known && policy == UnknownGid::kUnknownDropped) continue;
+    hg.from[kept] = static_cast<uint32_t>(dense_of_gid.GetOrZero(hg.gid_of_dense[hg.from[e]]));
+    hg.to[kept] = static_cast<uint32_t>(known ? dst : 0);
+    ++kept;
+  }
+  hg.from.resize(kept);
+  hg.to.resize(kept);
   return hg;
 }
 

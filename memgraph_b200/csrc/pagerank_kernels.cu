@@ -920,9 +920,16 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
       MGB_CUDA(cudaStreamWaitEvent(g.stream2, g.fork_ev, 0));
       forked = true;
     }
-    const int egrid = static_cast<int>(
-        std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(row_epilogue_kernel))),
-                 ceil_div(g.n_sell, kBlockThreads * kEpiRows)));
+    // Across GPUs this kernel IS the exchange (one NVLink store per peer per row): it is bound by the links, not by the
+    // SMs, and it must run NEXT TO the heavy-row kernels, not before or after them.  A full grid (4 CTAs/SM x 63
+    // registers) takes the whole register file, so the heavy kernel (8 CTAs/SM x 32 registers, also the whole file)
+    // only starts when it drains -- measured at 8 GPUs: 0.47 ms for the pair = 0.25 push + 0.22 heavy in sequence
+    // (profiles/r02_multi_gpu.md).  A small grid (MGB200_PUSH_CTAS per SM, default 1) leaves 6 of the heavy kernel's 8
+    // CTA slots free and keeps enough stores in flight to fill the links.
+    uint64_t egrid_cap = static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(row_epilogue_kernel)));
+    if (g.part_world > 1 && g.overlap_epilogue && g.tun.push_ctas > 0)
+      egrid_cap = std::min<uint64_t>(egrid_cap, static_cast<uint64_t>(g.sm_count) * g.tun.push_ctas);
+    const int egrid = static_cast<int>(std::min(egrid_cap, ceil_div(g.n_sell, kBlockThreads * kEpiRows)));
     MGB_CUDA(tick(Graph::kClsSellEpi, 0, es));
     row_epilogue_kernel<<<egrid, kBlockThreads, 0, es>>>(s.first_row, s.end_row, g.sell_sums, g.state, ep);
     MGB_CUDA(tick(Graph::kClsSellEpi, 1, es));
@@ -954,7 +961,11 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
                                         : h.window.path == kPathLookup ? heavy_segments_kernel<kPathLookup>
                                                                        : heavy_segments_kernel<kPathRange>;
     const void *hfn = reinterpret_cast<const void *>(heavy_fn);
-    int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_for(g, hfn)), ceil_div(g.n_seg, kWarpsPerBlock)));
+    uint64_t hgrid_cap = static_cast<uint64_t>(grid_for(g, hfn));
+    // leave register-file room for the push kernel's CTAs (63 registers x 256 threads each) next to this one
+    if (forked && g.part_world > 1 && g.tun.push_ctas > 0 && hgrid_cap > static_cast<uint64_t>(g.sm_count) * 2)
+      hgrid_cap -= static_cast<uint64_t>(g.sm_count) * 2;
+    int grid = static_cast<int>(std::min(hgrid_cap, ceil_div(g.n_seg, kWarpsPerBlock)));
     MGB_CUDA(tick(Graph::kClsHeavySeg, 0, g.stream));
     heavy_fn<<<grid, kBlockThreads, 0, g.stream>>>(h);
     MGB_CUDA(tick(Graph::kClsHeavySeg, 1, g.stream));

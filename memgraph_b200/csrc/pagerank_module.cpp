@@ -17,6 +17,7 @@
 #include <cstring>
 #include <exception>
 #include <stdexcept>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -34,6 +35,14 @@ constexpr const char *kArgMaxIterations = "max_iterations";
 constexpr const char *kArgDampingFactor = "damping_factor";
 constexpr const char *kArgStopEpsilon = "stop_epsilon";
 constexpr const char *kArgNumThreads = "num_of_threads";
+
+struct DeviceGraphCache {
+  std::mutex busy;
+  mgb200_graph *graph = nullptr;
+  uint64_t n = 0, m = 0, fp[2] = {0, 0}, hits = 0;
+  int device = -1;
+  ~DeviceGraphCache() { mgb200_graph_destroy(graph); }
+};
 
 int AbortTrampoline(void *user) { return MustAbort(static_cast<mgp_graph *>(user)) ? 1 : 0; }
 
@@ -56,20 +65,51 @@ std::vector<double> ComputeRanks(const HostGraph &hg, mgp_graph *graph, int64_t 
   const int gpus = gpus_env ? std::atoi(gpus_env) : 1;
   if (gpus > 1) {
     uint64_t iterations = 0;
-    const int rc = mgb200_pagerank_multi(n, hg.from.size(), hg.from.data(), hg.to.data(), &params, threads,
-                                         static_cast<uint32_t>(gpus), nullptr, ranks.data(), &iterations);
+    const int rc = mgb200_pagerank_multi_u32(n, hg.from.size(), hg.from.data(), hg.to.data(), &params, threads,
+                                             static_cast<uint32_t>(gpus), nullptr, ranks.data(), &iterations);
     if (rc != MGB200_OK) throw ModuleError(mgb200_last_error());
     return ranks;
   }
   const char *dev_env = std::getenv("MGB200_DEVICE");
   const int device = dev_env ? std::atoi(dev_env) : 0;
+  // MGB200_GRAPH_CACHE=1: keep the device-resident graph across CALLs.  The mgp ABI has no graph version, so the key is a
+  // 128-bit fingerprint of the dense COO just pulled (plus n, m, device): an unchanged graph skips the upload and the
+  // device build, a changed one replaces the slot.  One slot, taken with try_lock: a concurrent second query (the module is
+  // shared between sessions, src/query/plan/operator.cpp:7808-7829) simply builds its own throw-away graph.
+  static DeviceGraphCache cache;
+  const char *cache_env = std::getenv("MGB200_GRAPH_CACHE");
+  std::unique_lock<std::mutex> slot(cache.busy, std::defer_lock);
+  const bool use_cache = cache_env && cache_env[0] == '1' && slot.try_lock();
   mgb200_graph *dg = nullptr;
-  int rc = mgb200_graph_create_host(device, n, hg.from.size(), hg.from.data(), hg.to.data(), 0, 1, &dg);
-  if (rc != MGB200_OK) throw ModuleError(mgb200_last_error());
+  bool owned = true;
+  if (use_cache) {
+    uint64_t fp[2] = {0, 0};
+    if (mgb200_coo_fingerprint_u32(n, hg.from.size(), hg.from.data(), hg.to.data(), fp) != MGB200_OK)
+      throw ModuleError(mgb200_last_error());
+    if (cache.graph && cache.n == n && cache.m == hg.from.size() && cache.device == device && cache.fp[0] == fp[0] &&
+        cache.fp[1] == fp[1]) {
+      dg = cache.graph;
+      ++cache.hits;
+    } else {
+      mgb200_graph_destroy(cache.graph);
+      cache.graph = nullptr;
+      if (mgb200_graph_create_host_u32(device, n, hg.from.size(), hg.from.data(), hg.to.data(), 0, 1, &dg) != MGB200_OK)
+        throw ModuleError(mgb200_last_error());
+      cache.graph = dg;
+      cache.n = n;
+      cache.m = hg.from.size();
+      cache.device = device;
+      cache.fp[0] = fp[0];
+      cache.fp[1] = fp[1];
+    }
+    owned = false;
+  } else if (mgb200_graph_create_host_u32(device, n, hg.from.size(), hg.from.data(), hg.to.data(), 0, 1, &dg) != MGB200_OK) {
+    throw ModuleError(mgb200_last_error());
+  }
   mgb200_run_stats stats{};
-  rc = mgb200_pagerank_run(dg, &params, ranks.data(), &stats);
+  const int rc = mgb200_pagerank_run(dg, &params, ranks.data(), &stats);
   const std::string message = rc != MGB200_OK ? mgb200_last_error() : "";
-  mgb200_graph_destroy(dg);
+  if (owned) mgb200_graph_destroy(dg);
   if (rc != MGB200_OK) throw ModuleError(message);
   return ranks;
 }
