@@ -214,6 +214,7 @@ struct Graph {
   cudaEvent_t join_ev = nullptr;
   bool overlap_epilogue = true;
   bool stream_attr_set = false;
+  int table_attr_bytes[2] = {0, 0};  // dynamic shared memory already granted to sell_rows_table_kernel<range / flags>
   // MGB200_PUSH=copy: the exchange as peer copies of this partition's contiguous label slices on the copy engines
   // (one stream per peer), instead of NVLink stores issued by the epilogue kernels
   cudaStream_t copy_streams[kMaxPeers] = {};
@@ -225,10 +226,11 @@ struct Graph {
     bool multi_aware = true;     // MGB200_MULTI_AWARE=0: legacy "global label prefix is hot" on every partition
     bool force_multi_path = false;  // MGB200_FORCE_MULTI_PATH=1: run the multi-partition gather code on one GPU (measurement)
     bool stream_kernel = false;  // MGB200_SELL_KERNEL=stream
-    int push_ctas = 1;           // MGB200_PUSH_CTAS: CTAs per SM of the SELL epilogue + peer push on several partitions (0 = full grid)
+    uint32_t smem_table_kb = 0;  // MGB200_SMEM_TABLE_KB: shared-memory hot table of the SELL kernel (0 = off)
+    int push_ctas = 2;           // MGB200_PUSH_CTAS: CTAs per SM of the SELL epilogue + peer push on several partitions (0 = full grid)
     int sell_mode = -1;          // MGB200_SELL_MODE: 0 ticket queue, 1 static deal, -1 (default) by partition size
     bool global_order = false;   // MGB200_LABELLING=global: label = global degree order, blocks of 32 dealt (RowMap)
-    bool push_mask = false;      // MGB200_PUSH_MASK=1: push a contribution only to the partitions that gather it
+    bool push_mask = true;       // MGB200_PUSH_MASK=0: push every contribution to every peer (default: only to the partitions that gather it)
     bool lone_partition = false; // MGB200_LONE_PARTITION=1 (profiling only): run ONE partition of part_world without its
                                  // peers -- no stores to them, barrier of one; timings/ncu are real, ranks are NOT
     bool push_copy = false;      // MGB200_PUSH=copy (dealt contiguous ranges only)
@@ -242,6 +244,18 @@ struct Graph {
     if (tun.l1_hot_k < 0) return kNoL1Hints;
     const uint64_t v = static_cast<uint64_t>(tun.l1_hot_k) * 1024 / hot_divisor();
     return static_cast<uint32_t>(v < 0xFFFFFFF0ull ? v : 0xFFFFFFF0ull);
+  }
+  // labels in the shared-memory hot table: a multiple of 2 * partitions (every owner's window has an even size, a whole
+  // number of 16-byte TMA units on one partition); only with 30-bit labels on several partitions (the slot rides in
+  // the stored index), never with the per-gather owner lookup
+  uint32_t table_labels() const {
+    if (tun.smem_table_kb == 0 || tun.stream_kernel) return 0;
+    if (part_world > 1 && (!idx_flagged || map.global_order)) return 0;
+    if (part_world == 1 && (idx_flagged || tun.force_multi_path)) return 0;
+    const uint64_t unit = 2ull * part_world;
+    uint64_t labels = std::min<uint64_t>(static_cast<uint64_t>(tun.smem_table_kb) * 1024 / sizeof(double), n);
+    labels = labels / unit * unit;
+    return static_cast<uint32_t>(labels);
   }
   uint32_t l2_hot_labels() const {
     if (!tun.multi_aware) return 0xFFFFFFFFu;

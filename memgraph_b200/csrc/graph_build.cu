@@ -183,15 +183,21 @@ struct IndexFlags {
   Dealer deal;
   uint32_t l1_hot, l2_hot;  // Graph::l1_hot_labels() (kNoL1Hints -> no L1 flag is ever read), l2_hot_labels()
   uint32_t enabled;
+  uint32_t table_per_owner;  // > 0: the hottest labels of every owner live in the SELL kernel's shared-memory table;
+                             // their stored index is code 01 in bits 31/30 + the table slot (owner * per_owner + local)
   __device__ uint32_t operator()(uint32_t label) const {
     if (!enabled) return label;
     if (label >= deal.n) return label | kIdxL2Hot | kIdxL1Hot;  // the pad slot: one address, read by every slice
-    uint32_t s0 = 0;
+    uint32_t s0 = 0, owner = 0;
     for (uint32_t q = 1; q < deal.world; ++q) {
       const uint32_t s = static_cast<uint32_t>(deal.start(q));
-      if (label >= s) s0 = s;
+      if (label >= s) {
+        s0 = s;
+        owner = q;
+      }
     }
     const uint32_t local = label - s0;
+    if (local < table_per_owner) return kIdxL1Hot | (owner * table_per_owner + local);
     return label | (local < l2_hot ? kIdxL2Hot : 0u) | (l1_hot != kNoL1Hints && local < l1_hot ? kIdxL1Hot : 0u);
   }
 };
@@ -425,6 +431,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     if ((s = getenv("MGB200_IDX_FLAGS")) != nullptr) g.tun.idx_flags = atoi(s);
     if ((s = getenv("MGB200_SELL_MODE")) != nullptr) g.tun.sell_mode = atoi(s);
     if ((s = getenv("MGB200_PUSH_CTAS")) != nullptr) g.tun.push_ctas = std::max(0, atoi(s));
+    if ((s = getenv("MGB200_SMEM_TABLE_KB")) != nullptr) g.tun.smem_table_kb = static_cast<uint32_t>(std::min(224, std::max(0, atoi(s))));
     if ((s = getenv("MGB200_LABELLING")) != nullptr) g.tun.global_order = strcmp(s, "global") == 0;
     if ((s = getenv("MGB200_PUSH_MASK")) != nullptr) g.tun.push_mask = s[0] == '1';
     if ((s = getenv("MGB200_LONE_PARTITION")) != nullptr) g.tun.lone_partition = s[0] == '1';
@@ -454,7 +461,10 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   // They need two index bits (n < 2^30) and partition-aware thresholds; the TMA stream kernel reads raw indices.
   g.idx_flagged = (g.tun.idx_flags > 0 || (g.tun.idx_flags < 0 && g.part_world > 1)) && g.tun.multi_aware &&
                   !g.tun.global_order && !g.tun.stream_kernel && n < (1ull << 30);
-  const IndexFlags idx_flags{deal, g.l1_hot_labels(), g.l2_hot_labels(), g.idx_flagged ? 1u : 0u};
+  // (table_labels() needs idx_flagged, set just above; the heavy-row kernel has no table, so its indices keep labels)
+  const IndexFlags idx_flags_heavy{deal, g.l1_hot_labels(), g.l2_hot_labels(), g.idx_flagged ? 1u : 0u, 0u};
+  const IndexFlags idx_flags{deal, g.l1_hot_labels(), g.l2_hot_labels(), g.idx_flagged ? 1u : 0u,
+                             g.idx_flagged ? g.table_labels() / g.part_world : 0u};
   g.row_lo = 0;
   g.local_rows = 0;  // known once the degrees are (global order: depends on the heavy-row count of the whole graph)
 
@@ -667,7 +677,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     MGB_CUDA(keep_alloc(g, &g.heavy_ptr, g.n_heavy + 1));
     MGB_CUDA(cudaMemcpyAsync(g.heavy_ptr, row_ptr, (g.n_heavy + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     MGB_CUDA(keep_alloc(g, &g.heavy_idx, g.heavy_edges));
-    low32_kernel<<<blocks_for(g.heavy_edges, g.sm_count), kThreads, 0, st>>>(g.heavy_edges, ekey, idx_flags,
+    low32_kernel<<<blocks_for(g.heavy_edges, g.sm_count), kThreads, 0, st>>>(g.heavy_edges, ekey, idx_flags_heavy,
                                                                                    g.heavy_idx);
     MGB_CUDA(keep_alloc(g, &g.seg_first, g.n_heavy + 1));
     {

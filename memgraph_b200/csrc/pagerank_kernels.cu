@@ -84,6 +84,7 @@ struct GatherWindow {
   uint32_t l1_hot;       // local indices below this may allocate in L1
   uint32_t l2_hot;       // local indices below this are L2 evict_last (multi-partition form)
   uint32_t world;        // number of partitions
+  uint32_t table_n;      // labels held in the shared-memory hot table (0 = none); P partitions: table_n / P per owner
   uint32_t path;         // kernel instantiation: kPathRange / kPathLookup / kPathFlags (below)
   uint32_t start[kMaxPeers];  // first global label of every partition
 };
@@ -111,9 +112,20 @@ __device__ __forceinline__ GatherPolicy make_gather_policy(const double *contrib
   }
   return p;
 }
-template <int kPath, bool kSelectL2 = true>
+// The hottest labels live in shared memory (kTable): an L2 request is what the SMs run out of (one per SM per clock,
+// r01), and the degree-sorted labelling makes "hottest" a prefix -- 21 % of all gathers of RMAT-26 go to the first 16 K
+// labels, 27 % to the first 28 K (profiles/r01_topk_share.txt).  One partition: slot = label (label < table_n).  Several
+// partitions: the build stored the slot in the index itself, code 01 in bits 31/30 (graph_build.cu IndexFlags).
+template <int kPath, bool kSelectL2 = true, bool kTable = false>
 __device__ __forceinline__ double ld_contrib_at(const double *base, uint32_t src, const GatherPolicy &gp,
-                                                const GatherWindow &w) {
+                                                const GatherWindow &w, const double *table = nullptr) {
+  if (kTable) {
+    if (kPath == kPathFlags) {
+      if ((src >> 30) == 1u) return table[src & kIdxLabelMask];
+    } else if (src < w.table_n) {
+      return table[src];
+    }
+  }
   uint32_t label = src;
   uint64_t pol = gp.hot;
   bool l1_hot;
@@ -179,6 +191,35 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+
+// ---- mbarrier / TMA bulk-copy helpers (hot table fill here, index ring in sell_stream.cuh) ---------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+// TMA bulk copy global -> shared (1-D, bytes multiple of 16), completion counted on the mbarrier.
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar,
+                                            uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
 }
 
 // ---- per-row epilogue ------------------------------------------------------------------------------
@@ -377,14 +418,14 @@ constexpr int kSellUnroll = MGB_SELL_UNROLL;
 // order through a ticket counter, so a warp that drew cheap work (or sits on an SM with the longer way to L2) simply takes
 // more; the queue is software-pipelined (record of item i+1 and ticket of item i+2 in flight while item i is gathered).
 // mode 1 deals the items round-robin instead (no atomics) -- the A/B baseline of profiles/r02_sell_tickets.md.
-template <int kPath>
-__global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_kernel(const SellArgs a) {
-  if (ld_volatile_int(&a.state->done)) return;
+template <int kPath, bool kTable>
+__device__ __forceinline__ void sell_walk(const SellArgs &a, const double *table) {
   const int lane = threadIdx.x & 31;
+  const int warps_per_block = static_cast<int>(blockDim.x >> 5);
   const uint64_t pol = make_evict_first_policy();
   const GatherPolicy gpol = make_gather_policy(a.contrib_in, a.window);
-  unsigned long long static_next = static_cast<unsigned long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-  const unsigned long long warps_total = static_cast<unsigned long long>(gridDim.x) * kWarpsPerBlock;
+  unsigned long long static_next = static_cast<unsigned long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
+  const unsigned long long warps_total = static_cast<unsigned long long>(gridDim.x) * warps_per_block;
   auto draw = [&]() -> unsigned long long {
     if (a.mode == 1) {
       const unsigned long long t = static_next;
@@ -429,7 +470,7 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_
         if (k + kSellUnroll + j < ncols) nxt[j] = ld_index(p + static_cast<size_t>(k + kSellUnroll + j) * kSliceRows, pol);
 #pragma unroll
       for (int j = 0; j < kSellUnroll; ++j)
-        if (k + j < ncols) v[j] = ld_contrib_at<kPath>(a.contrib_in, src[j], gpol, a.window);
+        if (k + j < ncols) v[j] = ld_contrib_at<kPath, true, kTable>(a.contrib_in, src[j], gpol, a.window, table);
 #pragma unroll
       for (int j = 0; j < kSellUnroll; ++j) {
         if (k + j < ncols) {
@@ -463,6 +504,50 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_
       __threadfence();
     }
   }
+}
+
+
+template <int kPath>
+__global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_kernel(const SellArgs a) {
+  if (ld_volatile_int(&a.state->done)) return;
+  sell_walk<kPath, false>(a, nullptr);
+}
+
+// The same walk with the hot table: ONE 1024-thread CTA per SM (the same 32 warps as 4 x 256 threads) so that the SM
+// holds one copy of the table; filled once per launch -- one partition: TMA bulk copies (cp.async.bulk, 32 KiB each,
+// completion on an mbarrier, L2 evict-last) of the contiguous label prefix; several partitions: one window per owner,
+// whose first label is only 8-byte aligned, so the threads load it cooperatively.
+constexpr int kTableThreads = 1024;
+template <int kPath>
+__global__ void __launch_bounds__(kTableThreads, 1) sell_rows_table_kernel(const SellArgs a) {
+  extern __shared__ __align__(128) unsigned char table_smem[];
+  __shared__ __align__(8) unsigned long long fill_bar;
+  if (ld_volatile_int(&a.state->done)) return;
+  double *table = reinterpret_cast<double *>(table_smem);
+  const uint32_t table_n = a.window.table_n;
+  if (kPath == kPathFlags) {
+    const uint32_t per = table_n / a.window.world;
+    for (uint32_t q = 0; q < a.window.world; ++q)
+      for (uint32_t i = threadIdx.x; i < per; i += blockDim.x)
+        table[q * per + i] = __ldg(a.contrib_in + a.window.start[q] + i);
+    __syncthreads();
+  } else {
+    const uint32_t bar = smem_u32(&fill_bar);
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      uint64_t keep;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+      const uint32_t bytes = table_n * static_cast<uint32_t>(sizeof(double));
+      mbar_expect_tx(bar, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768u)
+        tma_load_1d(smem_u32(table_smem + off), reinterpret_cast<const unsigned char *>(a.contrib_in) + off,
+                    min(32768u, bytes - off), bar, keep);
+    }
+    __syncthreads();  // the barrier is initialised before anyone waits on it
+    mbar_wait(bar, 0);
+  }
+  sell_walk<kPath, true>(a, table);
 }
 
 #include "sell_stream.cuh"
@@ -751,6 +836,7 @@ GatherWindow make_window(const Graph &g) {
   w.world = g.part_world;
   w.l1_hot = g.l1_hot_labels();
   w.l2_hot = g.l2_hot_labels();
+  w.table_n = g.table_labels();
   // global-order labelling: "hot" is one label prefix on every partition -> the exact single-partition code
   w.path = g.idx_flagged ? kPathFlags
            : (g.tun.multi_aware && !g.map.global_order && (g.part_world > 1 || g.tun.force_multi_path)) ? kPathLookup
@@ -791,6 +877,30 @@ ZeroRanges make_zero_ranges(const Graph &g) {
 // the rank of a zero in-degree row once the loop has run at least once ((1-d)/N); 1/N if it never runs
 double zero_row_rank(const Graph &g, const IterateConfig &cfg) {
   return cfg.max_iterations == 0 ? 1.0 / static_cast<double>(g.n) : (1.0 - cfg.damping) / static_cast<double>(g.n);
+}
+
+// SELL rows: the plain kernel (4 x 256 threads per SM) or, with a hot table, one 1024-thread CTA per SM
+int launch_sell_rows(Graph &g, const SellArgs &s) {
+  const uint32_t table_n = s.window.table_n;
+  if (table_n > 0 && s.window.path != kPathLookup) {
+    void (*const fn)(SellArgs) = s.window.path == kPathFlags ? sell_rows_table_kernel<kPathFlags> : sell_rows_table_kernel<kPathRange>;
+    const int bytes = static_cast<int>(table_n * sizeof(double));
+    if (g.table_attr_bytes[s.window.path == kPathFlags] < bytes) {
+      MGB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      g.table_attr_bytes[s.window.path == kPathFlags] = bytes;
+    }
+    const int grid = static_cast<int>(std::min<uint64_t>(g.sm_count, ceil_div(g.sell_work, kTableThreads / 32)));
+    fn<<<grid, kTableThreads, bytes, g.stream>>>(s);
+  } else {
+    void (*const sell_fn)(SellArgs) = s.window.path == kPathFlags    ? sell_rows_kernel<kPathFlags>
+                                      : s.window.path == kPathLookup ? sell_rows_kernel<kPathLookup>
+                                                                     : sell_rows_kernel<kPathRange>;
+    const int grid = static_cast<int>(std::min(
+        static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_fn))), ceil_div(g.sell_work, kWarpsPerBlock)));
+    sell_fn<<<grid, kBlockThreads, 0, g.stream>>>(s);
+  }
+  MGB_CUDA(cudaGetLastError());
+  return MGB200_OK;
 }
 
 int launch_init(Graph &g, const IterateConfig &cfg) {
@@ -905,12 +1015,8 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
       const int sgrid = static_cast<int>(std::min<uint64_t>(g.sm_count, ceil_div(g.sell_items, kStreamWarps)));
       sell_stream_kernel<<<sgrid, kStreamThreads, kStreamSmemBytes, g.stream>>>(t);
     } else {
-      void (*const sell_fn)(SellArgs) = s.window.path == kPathFlags    ? sell_rows_kernel<kPathFlags>
-                                        : s.window.path == kPathLookup ? sell_rows_kernel<kPathLookup>
-                                                                       : sell_rows_kernel<kPathRange>;
-      const int grid = static_cast<int>(std::min(
-          static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_fn))), ceil_div(g.sell_work, kWarpsPerBlock)));
-      sell_fn<<<grid, kBlockThreads, 0, g.stream>>>(s);
+      const int rc = launch_sell_rows(g, s);
+      if (rc) return rc;
     }
     ++launches;
     MGB_CUDA(tick(Graph::kClsSell, 1, g.stream));
@@ -1037,12 +1143,8 @@ int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count) 
     s.window = window;
     s.state = g.state;
     s.sums = g.sell_sums;
-    void (*const sell_fn)(SellArgs) = window.path == kPathFlags    ? sell_rows_kernel<kPathFlags>
-                                      : window.path == kPathLookup ? sell_rows_kernel<kPathLookup>
-                                                                   : sell_rows_kernel<kPathRange>;
-    const int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_fn))),
-                                               ceil_div(g.sell_work, kWarpsPerBlock)));
-    sell_fn<<<grid, kBlockThreads, 0, g.stream>>>(s);
+    const int rc = launch_sell_rows(g, s);
+    if (rc) return rc;
     ++launches;
   }
   if (g.n_seg > 0) {

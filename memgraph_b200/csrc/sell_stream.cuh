@@ -51,34 +51,6 @@ struct SellStreamArgs {
   double *sums;  // [n_sell] per-row sums, consumed by sell_epilogue_kernel
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
-}
-// TMA bulk copy global -> shared (1-D, bytes multiple of 16), completion counted on the mbarrier.
-__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar,
-                                            uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(pol)
-      : "memory");
-}
 // Per-lane asynchronous 8-byte gather global -> shared (LDGSTS), with the gather window's L2 policy.
 __device__ __forceinline__ void gather_async_8(uint32_t dst_smem, const double *src, uint64_t pol) {
 #if MGB_GATHER_POLICY

@@ -160,7 +160,10 @@ def test_rmat_small_all_row_classes(mg, oracle, monkeypatch, heavy_min, seg):
                                  {"MGB200_SELL_MODE": "0", "MGB200_SELL_WORK_ITEMS": "37"},   # ticket queue
                                  {"MGB200_SELL_MODE": "1", "MGB200_SELL_WORK_ITEMS": "5"},    # static deal
                                  {"MGB200_SELL_MODE": "0", "MGB200_SELL_WORK_ITEMS": "100000"},
-                                 {"MGB200_OVERLAP_EPILOGUE": "0"}])
+                                 {"MGB200_OVERLAP_EPILOGUE": "0"},
+                                 {"MGB200_SMEM_TABLE_KB": "0"}, {"MGB200_SMEM_TABLE_KB": "1"}, {"MGB200_SMEM_TABLE_KB": "64"},
+                                 {"MGB200_SMEM_TABLE_KB": "200"},                              # hot table sizes (TMA fill)
+                                 {"MGB200_SMEM_TABLE_KB": "96", "MGB200_IDX_FLAGS": "1"}])
 def test_gather_path_variants_are_bit_identical(mg, oracle, monkeypatch, env):
     """How a gather learns its cache policy (range policy / hot flags baked into the stored index / per-gather owner
     lookup, with or without L1 hints), which kernel walks the SELL slices (LDG rows kernel / TMA + LDGSTS stream kernel)
