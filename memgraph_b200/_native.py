@@ -35,6 +35,16 @@ class KatzStats(ctypes.Structure):
                 ("kernel_launches", u64), ("tie_order_runs", u64)]
 
 
+class CugraphParams(ctypes.Structure):
+    _fields_ = [("max_iterations", u64), ("damping_factor", f64), ("stop_epsilon", f64), ("n_personalization", u64),
+                ("personalization_vertices", vp), ("personalization_values", vp)]
+
+
+class CugraphStats(ctypes.Structure):
+    _fields_ = [("iterations", u64), ("converged", i32), ("last_diff_sum", f64), ("iterate_ms", f64),
+                ("kernel_launches", u64)]
+
+
 KATZ_NOT_CONVERGED = 16
 ABORT_FN = ctypes.CFUNCTYPE(ctypes.c_int, vp)
 
@@ -75,6 +85,8 @@ EXPORTS = {
     "mgb200_katz_run": (i32, [vp, f64, f64, u64, vp, ctypes.POINTER(KatzStats)]),
     "mgb200_katz_centrality": (i32, [u64, u64, vp, vp, f64, f64, u64, vp, ctypes.POINTER(u64)]),
     "mgb200_katz_tie_order": (i32, [u64, vp, vp]),
+    # include/mgb200_personalized.h
+    "mgb200_cugraph_pagerank_run": (i32, [vp, ctypes.POINTER(CugraphParams), vp, ctypes.POINTER(CugraphStats)]),
     "mgb200_rmat_generate_device": (i32, [i32, u32, u64, u64, u64, f64, f64, f64, vp, vp]),
     "mgb200_rmat_generate_host": (i32, [u32, u64, u64, u64, f64, f64, f64, vp, vp]),
     "mgb200_device_malloc": (i32, [i32, ctypes.c_size_t, ctypes.POINTER(vp)]),

@@ -28,10 +28,10 @@ NVCC_FLAGS = [
     "-I", INCLUDE, "-I", CSRC,
     "-diag-suppress", "1444",  # cub::TransformInputIterator deprecation notice
 ]
-CUDA_SOURCES = ["pagerank_kernels.cu", "graph_build.cu", "capi.cu", "bfs.cu", "katz.cu"]
+CUDA_SOURCES = ["pagerank_kernels.cu", "graph_build.cu", "capi.cu", "bfs.cu", "katz.cu", "personalized.cu"]
 HEADERS = [os.path.join(CSRC, "core.hpp"), os.path.join(CSRC, "rmat.hpp"), os.path.join(CSRC, "sell_stream.cuh"),
            os.path.join(INCLUDE, "mgb200_pagerank.h"), os.path.join(INCLUDE, "mgb200_bfs.h"),
-           os.path.join(INCLUDE, "mgb200_katz.h"), os.path.join(CSRC, "katz_heap.hpp"),
+           os.path.join(INCLUDE, "mgb200_katz.h"), os.path.join(INCLUDE, "mgb200_personalized.h"), os.path.join(CSRC, "katz_heap.hpp"),
            os.path.join(INCLUDE, "mgp_abi.h"), os.path.join(CSRC, "mgp_module_common.hpp")]
 
 CORE_LIB = os.path.join(OUT, "libmgb200_pagerank.so")

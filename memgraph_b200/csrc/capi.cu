@@ -19,6 +19,7 @@
 
 #include "core.hpp"
 #include "mgb200_katz.h"
+#include "mgb200_personalized.h"
 #include "rmat.hpp"
 
 struct mgb200_graph {
@@ -185,6 +186,11 @@ int iterate(Graph &g, const mgb200_run_params &p, mgb200_run_stats &stats) {
 
 }  // namespace
 }  // namespace mgb200
+
+namespace mgb200 {
+int cugraph_pagerank_iterate(Graph &g, const mgb200_cugraph_params &prm, double *d_out_original_order,
+                             mgb200_cugraph_stats *stats);
+}
 
 using namespace mgb200;
 
@@ -731,6 +737,38 @@ int mgb200_katz_centrality(uint64_t n, uint64_t m, const uint64_t *from, const u
   mgb200_graph_destroy(g);
   if (iterations_out) *iterations_out = stats.iterations;
   return rc;
+}
+
+// ---- cuGraph-semantics PageRank (include/mgb200_personalized.h; kernels in personalized.cu) ---------------------
+
+int mgb200_cugraph_pagerank_run(mgb200_graph *h, const mgb200_cugraph_params *params, double *rank_out,
+                                mgb200_cugraph_stats *stats_out) {
+  if (!h || !params) return MGB200_ERR_INVALID_ARGUMENT;
+  Graph &g = h->g;
+  if (g.part_world != 1) {
+    set_error("mgb200_cugraph_pagerank_run needs a single-partition graph");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  if (g.n > 0 && !rank_out) {
+    set_error("rank_out is null");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  if (params->n_personalization && (!params->personalization_vertices || !params->personalization_values)) {
+    set_error("null personalization arrays");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  MGB_CUDA(cudaSetDevice(g.device));
+  if (g.n > 0 && !g.out_stage) MGB_CUDA(cudaMalloc(&g.out_stage, g.n * sizeof(double)));  // kept for the handle's life
+  mgb200_cugraph_stats stats{};
+  int rc = cugraph_pagerank_iterate(g, *params, g.out_stage, &stats);
+  if (rc) return rc;
+  if (g.n > 0) {
+    cudaError_t e = cudaMemcpyAsync(rank_out, g.out_stage, g.n * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(ranks D2H)", __FILE__, __LINE__);
+  }
+  if (stats_out) *stats_out = stats;
+  return MGB200_OK;
 }
 
 int mgb200_partition_range(uint64_t n, uint32_t part_world, uint32_t part_rank, uint64_t *first_label_out,

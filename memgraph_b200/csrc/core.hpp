@@ -300,7 +300,8 @@ struct IterateConfig {
 constexpr int kSumBlocks = 1024;
 int launch_init(Graph &g, const IterateConfig &cfg);
 int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *launch_count, uint64_t *spmv_count);
-int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count);  // SELL sums + heavy partials only
+// SELL sums + heavy segment partials (heavy_row_sums: also the heavy rows' sums, into g.heavy_sums)
+int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count, bool heavy_row_sums = false);
 int launch_barrier(Graph &g);
 int launch_sum_and_exchange(Graph &g);
 int launch_write_ranks_original_order(Graph &g, double *d_out);                   // single partition

@@ -1126,7 +1126,7 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
 // g.sell_sums, heavy segment partials into g.seg_partial (summed per row by the caller in segment order).  This is
 // y = A^T x for the rows of this partition with PageRank's kernels and cache policies; other SpMV-shaped paths hang
 // their own epilogue on it (Katz: omega_i = A^T omega_{i-1}, katz.cu).  Kernels return at once while state->done is set.
-int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count) {
+int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count, bool heavy_row_sums) {
   uint64_t launches = 0;
   const GatherWindow window = make_window(g);
   if (g.n_slices > 0) {
@@ -1168,6 +1168,14 @@ int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count) 
                                                ceil_div(g.n_seg, kWarpsPerBlock)));
     heavy_fn<<<grid, kBlockThreads, 0, g.stream>>>(h);
     ++launches;
+    if (heavy_row_sums) {
+      h.row_sums = g.heavy_sums;
+      const int rgrid = static_cast<int>(
+          std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_rowsum_kernel))),
+                   ceil_div(g.n_heavy, kWarpsPerBlock)));
+      heavy_rowsum_kernel<<<rgrid, kBlockThreads, 0, g.stream>>>(h);
+      ++launches;
+    }
   }
   MGB_CUDA(cudaGetLastError());
   if (launch_count) *launch_count += launches;

@@ -11,7 +11,7 @@ import conftest
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(REPO, "memgraph_b200", "_build", "libmgb200_pagerank.so")
-HEADERS = ["mgb200_pagerank.h", "mgb200_bfs.h", "mgb200_katz.h"]
+HEADERS = ["mgb200_pagerank.h", "mgb200_bfs.h", "mgb200_katz.h", "mgb200_personalized.h"]
 
 
 def declared_functions():
