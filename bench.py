@@ -346,23 +346,19 @@ def run_b200_arm(args):
     scale = args.scale
     n, m = 1 << scale, EDGE_FACTOR << scale
     t0 = time.perf_counter()
-    d_from = dev_alloc(N, lib, device, 4 * m)
-    d_to = dev_alloc(N, lib, device, 4 * m)
-    mg.rmat_edges_device(scale, m, d_from, d_to, seed=SEED, device=device)
-    gen_s = time.perf_counter() - t0
-    t0 = time.perf_counter()
     # profiling aid (--quick only): MGB200_LONE_WORLD=P runs partition 0 of P on ONE GPU without peers -- the per-GPU
     # kernels of an N=P run, under ncu if wanted; ranks are meaningless, timings are not
     lone = int(os.environ.get("MGB200_LONE_WORLD", "0")) if (args.quick and world == 1) else 0
     if lone > 1:
         os.environ["MGB200_LONE_PARTITION"] = "1"
-    g = mg.PageRankGraph.from_device(n, m, d_from, d_to, device=device, part_rank=rank,
-                                     part_world=lone if lone > 1 else world)
+    # every rank builds its partition straight from the generator, a chunk of edges at a time (no device ever holds the
+    # whole edge list: graph size scales with the GPU count)
+    g = mg.PageRankGraph.from_rmat(scale, m, seed=SEED, device=device, part_rank=rank,
+                                   part_world=lone if lone > 1 else world)
     build_wall_s = time.perf_counter() - t0
-    lib.mgb200_device_free(device, d_from)
-    lib.mgb200_device_free(device, d_to)
+    gen_s = 0.0
     info = g.info
-    log(f"[rank {rank}] RMAT scale-{scale}: gen {gen_s:.2f}s, build {build_wall_s:.2f}s (device {info['build_ms']:.0f} ms), "
+    log(f"[rank {rank}] RMAT scale-{scale}: generate + build {build_wall_s:.2f}s (device {info['build_ms']:.0f} ms), "
         f"rows {info['local_rows']} edges {info['local_edges']} heavy_rows {info['heavy_rows']} "
         f"heavy_edges {info['heavy_edges']} segs {info['heavy_segments']} sell_rows {info['sell_rows']} "
         f"sell_entries {info['sell_entries']} zero_rows {info['zero_rows']} resident {info['resident_bytes']/2**30:.2f} GiB")
@@ -501,7 +497,7 @@ def run_b200_arm(args):
     # its (vertex, rank) slice into a full-length vector (disjoint slices, summed over NVLink), rank 0 rebuilds the
     # WHOLE graph as one partition on its own GPU, runs the same call and compares all N ranks.
     parity = None
-    if world > 1 and not args.no_parity:
+    if world > 1 and not args.no_parity and scale <= 27:  # the single-GPU reference build must fit one device
         import torch
         dev = torch.device("cuda", device)
         full = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -513,12 +509,7 @@ def run_b200_arm(args):
         dist.all_reduce(owned)
         if rank == 0:
             t0 = time.perf_counter()
-            d_from = dev_alloc(N, lib, device, 4 * m)
-            d_to = dev_alloc(N, lib, device, 4 * m)
-            mg.rmat_edges_device(scale, m, d_from, d_to, seed=SEED, device=device)
-            g1 = mg.PageRankGraph.from_device(n, m, d_from, d_to, device=device, part_rank=0, part_world=1)
-            lib.mgb200_device_free(device, d_from)
-            lib.mgb200_device_free(device, d_to)
+            g1 = mg.PageRankGraph.from_rmat(scale, m, seed=SEED, device=device)
             single = torch.empty(n, dtype=torch.float64, device=dev)
             p1, _cb1 = make_params(ITERATIONS, DAMPING, 0.0, on_device=True)
             st1 = N.RunStatsC()

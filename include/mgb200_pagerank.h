@@ -108,7 +108,7 @@ int mgb200_graph_create_host(int device, uint64_t n, uint64_t m, const uint64_t 
 
 /* Same for callers that hold 32-bit dense ids already (the query module narrows while it pulls the graph through
  * the mgp iterators): half the host memory, nothing to narrow.  Both host forms stage through pinned, double-buffered
- * chunks filled by a few host threads (MGB200_INGEST_THREADS, default min(16, cores/2)) while the previous chunk is
+ * chunks filled by a few host threads (MGB200_INGEST_THREADS, default min(32, cores/2)) while the previous chunk is
  * on the wire: one pass, 8 bytes per edge over PCIe. */
 int mgb200_graph_create_host_u32(int device, uint64_t n, uint64_t m, const uint32_t *from, const uint32_t *to,
                                  uint32_t part_rank, uint32_t part_world, mgb200_graph **out);
@@ -203,6 +203,12 @@ int mgb200_rmat_generate_device(int device, uint32_t scale, uint64_t first_edge,
                                 double a, double b, double c, uint32_t *d_from, uint32_t *d_to);
 int mgb200_rmat_generate_host(uint32_t scale, uint64_t first_edge, uint64_t count, uint64_t seed, double a, double b,
                               double c, uint64_t *from, uint64_t *to);
+
+/* A partition of the RMAT graph built straight from the generator, a chunk (2^27 edges) at a time, in two passes
+ * (degrees, then the edges this partition owns): no device ever holds the whole edge list, so the graph a machine can
+ * take grows with its GPU count -- every partition still SCANS all edges, it does not keep them. */
+int mgb200_graph_create_rmat(int device, uint32_t scale, uint64_t edge_count, uint64_t seed, double a, double b, double c,
+                             uint32_t part_rank, uint32_t part_world, mgb200_graph **out);
 
 /* ---- small device-memory helpers so a ctypes caller needs nothing but this library -------------- */
 int mgb200_device_malloc(int device, size_t bytes, void **ptr_out);

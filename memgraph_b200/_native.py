@@ -87,6 +87,7 @@ EXPORTS = {
     "mgb200_katz_tie_order": (i32, [u64, vp, vp]),
     # include/mgb200_personalized.h
     "mgb200_cugraph_pagerank_run": (i32, [vp, ctypes.POINTER(CugraphParams), vp, ctypes.POINTER(CugraphStats)]),
+    "mgb200_graph_create_rmat": (i32, [i32, u32, u64, u64, f64, f64, f64, u32, u32, ctypes.POINTER(vp)]),
     "mgb200_rmat_generate_device": (i32, [i32, u32, u64, u64, u64, f64, f64, f64, vp, vp]),
     "mgb200_rmat_generate_host": (i32, [u32, u64, u64, u64, f64, f64, f64, vp, vp]),
     "mgb200_device_malloc": (i32, [i32, ctypes.c_size_t, ctypes.POINTER(vp)]),

@@ -57,6 +57,54 @@ __global__ void rmat_kernel(uint32_t scale, uint64_t first_edge, uint64_t count,
   }
 }
 
+// ---- edge sources of the build (core.hpp EdgeSource) ------------------------------------------------------------
+uint64_t build_chunk_edges(uint64_t fallback) {
+  const char *s = getenv("MGB200_BUILD_CHUNK_EDGES");  // tests shrink it to force many chunks
+  const unsigned long long v = s ? strtoull(s, nullptr, 10) : 0ull;
+  return v ? v : fallback;
+}
+
+struct DeviceArrays final : EdgeSource {  // the whole COO is resident: chunks are views
+  const uint32_t *from, *to;
+  DeviceArrays(uint64_t count, const uint32_t *f, const uint32_t *t) : from(f), to(t) {
+    m = count;
+    chunk_edges = build_chunk_edges(count);
+  }
+  int get(uint64_t first, uint64_t, const uint32_t **f, const uint32_t **t, cudaStream_t) override {
+    *f = from + first;
+    *t = to + first;
+    return MGB200_OK;
+  }
+};
+
+struct RmatStream final : EdgeSource {  // the synthetic workload, generated chunk by chunk: no COO is ever materialised
+  uint32_t scale;
+  uint64_t seed;
+  RmatThresholds thr;
+  uint32_t *buf_from = nullptr, *buf_to = nullptr;
+  RmatStream(uint32_t scale_, uint64_t count, uint64_t seed_, double a, double b, double c)
+      : scale(scale_), seed(seed_), thr(rmat_thresholds(a, b, c)) {
+    m = count;
+    chunk_edges = std::min<uint64_t>(std::max<uint64_t>(count, 1), build_chunk_edges(1ull << 27));
+  }
+  ~RmatStream() override {
+    cudaFree(buf_from);
+    cudaFree(buf_to);
+  }
+  int get(uint64_t first, uint64_t count, const uint32_t **f, const uint32_t **t, cudaStream_t st) override {
+    if (!buf_from) {
+      MGB_CUDA(cudaMalloc(&buf_from, chunk_edges * sizeof(uint32_t)));
+      MGB_CUDA(cudaMalloc(&buf_to, chunk_edges * sizeof(uint32_t)));
+    }
+    const int blocks = static_cast<int>(std::min<uint64_t>((count + 255) / 256, 148ull * 32));
+    rmat_kernel<<<blocks, 256, 0, st>>>(scale, first, count, seed, thr, buf_from, buf_to);
+    MGB_CUDA(cudaGetLastError());
+    *f = buf_from;
+    *t = buf_to;
+    return MGB200_OK;
+  }
+};
+
 int check_device(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -232,7 +280,45 @@ int mgb200_graph_create_device(int device, uint64_t n, uint64_t m, const uint32_
   h->g.m = m;
   h->g.part_rank = part_rank;
   h->g.part_world = part_world;
-  rc = build_graph(h->g, d_from, d_to);
+  DeviceArrays source(m, d_from, d_to);
+  rc = build_graph(h->g, source);
+  if (rc) {
+    free_graph(h->g);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return MGB200_OK;
+}
+
+int mgb200_graph_create_rmat(int device, uint32_t scale, uint64_t edge_count, uint64_t seed, double a, double b, double c,
+                             uint32_t part_rank, uint32_t part_world, mgb200_graph **out) {
+  if (!out) return MGB200_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (scale == 0 || scale > 31) {
+    set_error("rmat: scale must be in [1, 31]");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  const uint64_t n = 1ull << scale;
+  int rc = validate_sizes(n, part_rank, part_world);
+  if (rc) return rc;
+  rc = check_device(device);
+  if (rc) return rc;
+  auto *h = new (std::nothrow) mgb200_graph();
+  if (!h) {
+    set_error("out of host memory");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  h->g.device = device;
+  h->g.n = n;
+  h->g.m = edge_count;
+  h->g.part_rank = part_rank;
+  h->g.part_world = part_world;
+  cudaSetDevice(device);
+  {
+    RmatStream source(scale, edge_count, seed, a, b, c);
+    rc = build_graph(h->g, source);
+  }
   if (rc) {
     free_graph(h->g);
     delete h;
@@ -293,7 +379,7 @@ unsigned ingest_threads() {
   const char *s = getenv("MGB200_INGEST_THREADS");
   if (s && atoi(s) > 0) return static_cast<unsigned>(std::min(atoi(s), 64));
   const unsigned hw = std::thread::hardware_concurrency();
-  return std::max(1u, std::min(16u, hw / 2));
+  return std::max(1u, std::min(32u, hw / 2));
 }
 
 template <typename T>

@@ -285,8 +285,19 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
     if (_e != cudaSuccess) return ::mgb200::cuda_fail(_e, #expr, __FILE__, __LINE__); \
   } while (0)
 
+// Where the build reads the COO from, a chunk at a time (graph_build.cu walks it twice: degrees, then the edges this
+// partition owns).  With several partitions nobody has to hold the whole edge list on a device: the transient is one
+// chunk plus the owned edges, so the graph size scales with the number of GPUs.
+struct EdgeSource {
+  uint64_t m = 0;            // edges in total
+  uint64_t chunk_edges = 0;  // largest count the build may ask for
+  virtual ~EdgeSource() = default;
+  // device pointers to edges [first, first + count), valid until the next call (work is enqueued on `st`)
+  virtual int get(uint64_t first, uint64_t count, const uint32_t **from, const uint32_t **to, cudaStream_t st) = 0;
+};
+
 // graph_build.cu
-int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to);
+int build_graph(Graph &g, EdgeSource &edges);
 void free_graph(Graph &g);
 int narrow_edges_u64_to_u32(int device, cudaStream_t stream, uint64_t n, uint64_t count, const uint64_t *d_in,
                             uint32_t *d_out, int *d_bad_flag);

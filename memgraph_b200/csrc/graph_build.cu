@@ -404,7 +404,7 @@ void free_graph(Graph &g) {
   if (g.stream) cudaStreamDestroy(g.stream);
 }
 
-int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
+int build_graph(Graph &g, EdgeSource &edges) {
   MGB_CUDA(cudaSetDevice(g.device));
   cudaDeviceProp prop{};
   MGB_CUDA(cudaGetDeviceProperties(&prop, g.device));
@@ -507,7 +507,14 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   MGB_CUDA(cudaMemsetAsync(outdeg, 0, n * sizeof(uint32_t), st));
   MGB_CUDA(cudaMemsetAsync(indeg, 0, n * sizeof(uint32_t), st));
   MGB_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
-  if (m) degree_kernel<<<blocks_for(m, g.sm_count), kThreads, 0, st>>>(m, n, d_from, d_to, outdeg, indeg, bad);
+  const uint64_t chunk_cap = std::max<uint64_t>(1, std::min<uint64_t>(edges.chunk_edges ? edges.chunk_edges : m, std::max<uint64_t>(m, 1)));
+  for (uint64_t first = 0; first < m; first += chunk_cap) {  // pass 1 over the edge list: degrees
+    const uint64_t cnt = std::min(chunk_cap, m - first);
+    const uint32_t *d_from = nullptr, *d_to = nullptr;
+    const int grc = edges.get(first, cnt, &d_from, &d_to, st);
+    if (grc) return grc;
+    degree_kernel<<<blocks_for(cnt, g.sm_count), kThreads, 0, st>>>(cnt, n, d_from, d_to, outdeg, indeg, bad);
+  }
   int bad_host = 0;
   MGB_CUDA(cudaMemcpyAsync(&bad_host, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   MGB_CUDA(cudaStreamSynchronize(st));
@@ -576,7 +583,7 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
     const uint64_t words = (g.local_rows + 3) / 4;
     MGB_CUDA(keep_alloc(g, &g.need_mask, words));
     MGB_CUDA(cudaMemsetAsync(g.need_mask, 0, words * sizeof(uint32_t), st));
-    need_mask_kernel<<<blocks_for(m, g.sm_count), kThreads, 0, st>>>(m, d_from, d_to, g.label_of, map, g.need_mask);
+    // filled in pass 2 over the edge list, next to the owned-edge extraction
   }
 
   // 4. class boundaries and local edge count
@@ -629,13 +636,19 @@ int build_graph(Graph &g, const uint32_t *d_from, const uint32_t *d_to) {
   uint64_t *ekey = nullptr, *ekey_alt = nullptr;
   MGB_CUDA(tmp.alloc(&ekey, g.local_edges));
   MGB_CUDA(tmp.alloc(&ekey_alt, g.local_edges));
-  if (m) {
+  if (m && g.part_world > 1) MGB_CUDA(cudaMemsetAsync(counts + 3, 0, sizeof(unsigned long long), st));
+  for (uint64_t first = 0; first < m; first += chunk_cap) {  // pass 2 over the edge list: who reads what, owned edges
+    const uint64_t cnt = std::min(chunk_cap, m - first);
+    const uint32_t *d_from = nullptr, *d_to = nullptr;
+    const int grc = edges.get(first, cnt, &d_from, &d_to, st);
+    if (grc) return grc;
+    if (g.need_mask)
+      need_mask_kernel<<<blocks_for(cnt, g.sm_count), kThreads, 0, st>>>(cnt, d_from, d_to, g.label_of, map, g.need_mask);
     if (g.part_world == 1) {
-      edge_key_all_kernel<<<blocks_for(m, g.sm_count), kThreads, 0, st>>>(m, d_from, d_to, g.label_of, ekey);
+      edge_key_all_kernel<<<blocks_for(cnt, g.sm_count), kThreads, 0, st>>>(cnt, d_from, d_to, g.label_of, ekey + first);
     } else {
-      MGB_CUDA(cudaMemsetAsync(counts + 3, 0, sizeof(unsigned long long), st));
-      edge_key_owned_kernel<<<blocks_for(m, g.sm_count), kThreads, 0, st>>>(m, d_from, d_to, g.label_of, map, row_hi,
-                                                                           ekey, counts + 3);
+      edge_key_owned_kernel<<<blocks_for(cnt, g.sm_count), kThreads, 0, st>>>(cnt, d_from, d_to, g.label_of, map, row_hi,
+                                                                             ekey, counts + 3);
     }
   }
   if (g.local_edges) {

@@ -101,6 +101,18 @@ class PageRankGraph:
                                                 ctypes.byref(h)))
         self._finish(h, device)
 
+    @classmethod
+    def from_rmat(cls, scale, number_of_edges=None, seed=42, device=0, part_rank=0, part_world=1, a=0.57, b=0.19, c=0.19):
+        """The synthetic RMAT graph built straight from the generator, a chunk at a time: no device holds the
+        whole edge list (mgb200_graph_create_rmat)."""
+        self = cls.__new__(cls)
+        h = N.vp()
+        m = (16 << scale) if number_of_edges is None else int(number_of_edges)
+        _check(N.lib().mgb200_graph_create_rmat(device, int(scale), m, int(seed), a, b, c, part_rank, part_world,
+                                                ctypes.byref(h)))
+        self._finish(h, device)
+        return self
+
     def _finish(self, h, device):
         self._h = h
         self.device = device

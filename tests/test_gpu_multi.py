@@ -155,3 +155,33 @@ def test_abort_is_collective_and_handles_stay_usable():
         g.close()
     ref, _ = Oracle().pagerank(n, f, t, max_iterations=20, stop_epsilon=0.0)
     assert float(np.max(np.abs(out - ref) / ref)) < REL_TOL
+
+
+def test_partitions_built_from_the_generator_stream(monkeypatch):
+    """mgb200_graph_create_rmat: every partition walks the generator a chunk at a time and keeps only its own edges
+    (no device holds the whole COO).  Same ranks as the oracle on the materialised graph."""
+    world = 2
+    if _device_count() < world:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("MGB200_BUILD_CHUNK_EDGES", "50000")
+    import memgraph_b200 as mg
+    scale = 16
+    n, m = 1 << scale, 16 << scale
+    graphs = [mg.PageRankGraph.from_rmat(scale, m, device=q, part_rank=q, part_world=world) for q in range(world)]
+    for g in graphs:
+        g.connect_peers(local_graphs=graphs)
+    results = [None] * world
+    def work(q):
+        results[q] = graphs[q].run_partition(max_iterations=20, stop_epsilon=0.0)
+    threads = [threading.Thread(target=work, args=(q,)) for q in range(world)]
+    [th.start() for th in threads]
+    [th.join(timeout=120) for th in threads]
+    out = np.full(n, np.nan)
+    for ranks, verts, st in results:
+        out[verts.astype(np.int64)] = ranks
+    assert sum(g.info["local_edges"] for g in graphs) == m
+    for g in graphs:
+        g.close()
+    f, t = mg.rmat_edges_host(scale, m)
+    ref, _ = Oracle().pagerank(n, f, t, max_iterations=20, stop_epsilon=0.0)
+    assert float(np.max(np.abs(out - ref) / ref)) < REL_TOL
