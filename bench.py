@@ -361,7 +361,8 @@ def run_b200_arm(args):
     log(f"[rank {rank}] RMAT scale-{scale}: generate + build {build_wall_s:.2f}s (device {info['build_ms']:.0f} ms), "
         f"rows {info['local_rows']} edges {info['local_edges']} heavy_rows {info['heavy_rows']} "
         f"heavy_edges {info['heavy_edges']} segs {info['heavy_segments']} sell_rows {info['sell_rows']} "
-        f"sell_entries {info['sell_entries']} zero_rows {info['zero_rows']} resident {info['resident_bytes']/2**30:.2f} GiB")
+        f"sell_entries {info['sell_entries']} zero_rows {info['zero_rows']} resident {info['resident_bytes']/2**30:.2f} GiB "
+        f"build peak {info['build_peak_bytes']/2**30:.2f} GiB")
 
     if world > 1:
         import torch
@@ -429,6 +430,8 @@ def run_b200_arm(args):
                   "edges_per_s": value, "sell_kernel_ms": kernel_ms / max(kernel_launches, 1),
                   "class_ms_per_iteration": {k: round(float(v) / (args.steps * ITERATIONS), 4)
                                              for k, v in zip(CLASS_NAMES, class_ms)},
+                  "build_wall_s": build_wall_s, "resident_gib": info["resident_bytes"] / 2**30,
+                  "build_peak_gib": info["build_peak_bytes"] / 2**30, "local_edges": info["local_edges"],
                   "tag": os.environ.get("MGB200_TAG", "")})
         if dist is not None:
             dist.barrier()
@@ -569,7 +572,7 @@ def run_b200_arm(args):
         "config": {"workload": f"PageRank RMAT scale-{scale} EF16 (N={n}, E={m}), {ITERATIONS} iterations, d={DAMPING}, "
                                f"stop_epsilon=0, seed {SEED}", "parallelism": f"vertex-partition x{world}",
                    "l2": "inputs larger than L2 (index stream %.1f GB/iteration)" % (4 * m / 1e9),
-                   "graph_gen_s": gen_s, "graph_build_ms": info["build_ms"],
+                   "graph_build_wall_s": build_wall_s, "graph_build_ms": info["build_ms"], "build_peak_gib": info["build_peak_bytes"] / 2**30,
                    "heavy_rows": info["heavy_rows"], "heavy_edges": info["heavy_edges"], "sell_rows": info["sell_rows"],
                    "sell_entries": info["sell_entries"], "zero_rows": info["zero_rows"]},
         "ms_per_iteration": total_ms / args.steps / ITERATIONS,

@@ -64,6 +64,7 @@ typedef struct mgb200_graph_info {
   uint64_t resident_bytes; /* device bytes held by the handle after build             */
   double build_ms;         /* device time of the CSR/SELL build                       */
   double upload_ms;        /* host COO -> device, wall clock (0 for create_device)    */
+  uint64_t build_peak_bytes; /* device memory in use at the build's high-water mark   */
 } mgb200_graph_info;
 
 typedef struct mgb200_run_stats {

@@ -17,7 +17,7 @@ class GraphInfo(ctypes.Structure):
     _fields_ = [("node_count", u64), ("edge_count", u64), ("part_rank", u32), ("part_world", u32),
                 ("local_rows", u64), ("local_edges", u64), ("heavy_rows", u64), ("heavy_edges", u64),
                 ("heavy_segments", u64), ("sell_rows", u64), ("sell_slices", u64), ("sell_entries", u64),
-                ("zero_rows", u64), ("resident_bytes", u64), ("build_ms", f64), ("upload_ms", f64)]
+                ("zero_rows", u64), ("resident_bytes", u64), ("build_ms", f64), ("upload_ms", f64), ("build_peak_bytes", u64)]
 
 
 class RunStatsC(ctypes.Structure):

@@ -533,6 +533,7 @@ int mgb200_graph_get_info(const mgb200_graph *h, mgb200_graph_info *info) {
   info->resident_bytes = g.resident_bytes;
   info->build_ms = g.build_ms;
   info->upload_ms = g.upload_ms;
+  info->build_peak_bytes = g.build_peak_bytes;
   return MGB200_OK;
 }
 

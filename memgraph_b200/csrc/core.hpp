@@ -205,6 +205,7 @@ struct Graph {
   bool poisoned = false;  // a peer barrier timed out: the partitions' barrier counters may disagree; runs are refused
 
   uint64_t resident_bytes = 0;
+  uint64_t build_peak_bytes = 0;  // highest device memory in use seen during the build (transients included)
   double build_ms = 0.0;
   double upload_ms = 0.0;  // host COO -> device (mgb200_graph_create_host*), wall clock
   cudaEvent_t ev[4] = {};
@@ -215,11 +216,6 @@ struct Graph {
   bool overlap_epilogue = true;
   bool stream_attr_set = false;
   int table_attr_bytes[2] = {0, 0};  // dynamic shared memory already granted to sell_rows_table_kernel<range / flags>
-  // MGB200_PUSH=copy: the exchange as peer copies of this partition's contiguous label slices on the copy engines
-  // (one stream per peer), instead of NVLink stores issued by the epilogue kernels
-  cudaStream_t copy_streams[kMaxPeers] = {};
-  cudaEvent_t copy_done[kMaxPeers] = {};
-  cudaEvent_t sell_ready_ev = nullptr, heavy_ready_ev = nullptr;
   struct Tunables {  // environment, read once per graph in build_graph()
     uint64_t l2_hot_mb = 64;     // MGB200_L2_HOT_MB: evict-last window of the gathered vector (64 = effective L2, l2_bench)
     long l1_hot_k = 16;          // MGB200_L1_HOT_K: hottest labels (x1024) allowed to allocate in L1; <0 = no L1 hints
@@ -233,7 +229,6 @@ struct Graph {
     bool push_mask = true;       // MGB200_PUSH_MASK=0: push every contribution to every peer (default: only to the partitions that gather it)
     bool lone_partition = false; // MGB200_LONE_PARTITION=1 (profiling only): run ONE partition of part_world without its
                                  // peers -- no stores to them, barrier of one; timings/ncu are real, ranks are NOT
-    bool push_copy = false;      // MGB200_PUSH=copy (dealt contiguous ranges only)
     int idx_flags = -1;          // MGB200_IDX_FLAGS: 1 bake hotness into the indices, 0 never, -1 (default) see build_graph
     unsigned long long barrier_timeout_ms = 20000;  // MGB200_BARRIER_TIMEOUT_MS
   } tun;

@@ -341,6 +341,12 @@ cudaError_t keep_alloc(Graph &g, T **out, uint64_t count) {
   return e;
 }
 
+// peak device memory in use during the build (whole device, so other handles of the process count too)
+void note_mem(Graph &g) {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) g.build_peak_bytes = std::max<uint64_t>(g.build_peak_bytes, total_b - free_b);
+}
+
 uint32_t env_u32(const char *name, uint32_t fallback) {
   const char *s = getenv(name);
   if (!s || !*s) return fallback;
@@ -394,12 +400,6 @@ void free_graph(Graph &g) {
     if (e) cudaEventDestroy(e);
   if (g.fork_ev) cudaEventDestroy(g.fork_ev);
   if (g.join_ev) cudaEventDestroy(g.join_ev);
-  for (auto &e : g.copy_done)
-    if (e) cudaEventDestroy(e);
-  if (g.sell_ready_ev) cudaEventDestroy(g.sell_ready_ev);
-  if (g.heavy_ready_ev) cudaEventDestroy(g.heavy_ready_ev);
-  for (auto &cs : g.copy_streams)
-    if (cs) cudaStreamDestroy(cs);
   if (g.stream2) cudaStreamDestroy(g.stream2);
   if (g.stream) cudaStreamDestroy(g.stream);
 }
@@ -418,8 +418,6 @@ int build_graph(Graph &g, EdgeSource &edges) {
   }
   MGB_CUDA(cudaEventCreateWithFlags(&g.fork_ev, cudaEventDisableTiming));
   MGB_CUDA(cudaEventCreateWithFlags(&g.join_ev, cudaEventDisableTiming));
-  MGB_CUDA(cudaEventCreateWithFlags(&g.sell_ready_ev, cudaEventDisableTiming));
-  MGB_CUDA(cudaEventCreateWithFlags(&g.heavy_ready_ev, cudaEventDisableTiming));
   {
     const char *s = getenv("MGB200_OVERLAP_EPILOGUE");
     g.overlap_epilogue = !(s && s[0] == '0');
@@ -435,7 +433,6 @@ int build_graph(Graph &g, EdgeSource &edges) {
     if ((s = getenv("MGB200_LABELLING")) != nullptr) g.tun.global_order = strcmp(s, "global") == 0;
     if ((s = getenv("MGB200_PUSH_MASK")) != nullptr) g.tun.push_mask = s[0] == '1';
     if ((s = getenv("MGB200_LONE_PARTITION")) != nullptr) g.tun.lone_partition = s[0] == '1';
-    if ((s = getenv("MGB200_PUSH")) != nullptr) g.tun.push_copy = strcmp(s, "copy") == 0;
     if ((s = getenv("MGB200_BARRIER_TIMEOUT_MS")) != nullptr) {
       const unsigned long long ms = strtoull(s, nullptr, 10);
       if (ms) g.tun.barrier_timeout_ms = ms;
@@ -651,6 +648,7 @@ int build_graph(Graph &g, EdgeSource &edges) {
                                                                              ekey, counts + 3);
     }
   }
+  note_mem(g);
   if (g.local_edges) {
     cub::DoubleBuffer<uint64_t> kb(ekey, ekey_alt);
     size_t bytes = 0;
@@ -659,6 +657,7 @@ int build_graph(Graph &g, EdgeSource &edges) {
     void *cub_tmp = nullptr;
     MGB_CUDA(tmp.alloc(reinterpret_cast<char **>(&cub_tmp), bytes));
     MGB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, bytes, kb, g.local_edges, 0, end_bit, st));
+    note_mem(g);
     ekey = kb.Current();
   }
 
@@ -767,6 +766,7 @@ int build_graph(Graph &g, EdgeSource &edges) {
     work_item_kernel<<<(g.sell_work + kThreads - 1) / kThreads, kThreads, 0, st>>>(g.sell_work, g.sell_work_begin,
                                                                                   g.sell_colbase, g.sell_work_items);
   }
+  note_mem(g);
   MGB_CUDA(cudaGetLastError());
   MGB_CUDA(cudaEventRecord(g.ev[1], st));
   MGB_CUDA(cudaStreamSynchronize(st));

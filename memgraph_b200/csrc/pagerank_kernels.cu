@@ -234,7 +234,7 @@ struct RowEpilogue {
   int world;
   int self;                // this partition
   const uint8_t *need;     // [local_rows] bit q: partition q gathers this row's contribution; nullptr = everyone
-  uint32_t store_mask;     // bit q: the epilogue stores into partition q's buffer (all ones; self only under MGB200_PUSH=copy)
+  uint32_t store_mask;     // bit q: the epilogue stores into partition q's buffer (all ones; self only in the lone-partition profiling mode)
 };
 
 // max over the block of the rows' |delta| (callers start from -1.0 = "none seen"; NaN deltas never replace it, like
@@ -817,9 +817,7 @@ RowEpilogue make_epilogue(const Graph &g, uint64_t it, const IterateConfig &cfg)
   ep.world = static_cast<int>(g.part_world);
   ep.self = static_cast<int>(g.part_rank);
   ep.need = reinterpret_cast<const uint8_t *>(g.need_mask);
-  ep.store_mask = ((g.tun.push_copy && g.part_world > 1 && !g.map.global_order) || g.tun.lone_partition)
-                      ? (1u << g.part_rank)
-                      : 0xFFFFFFFFu;
+  ep.store_mask = g.tun.lone_partition ? (1u << g.part_rank) : 0xFFFFFFFFu;
   const int out_parity = static_cast<int>((it + 1) & 1ull);
   for (int q = 0; q < kMaxPeers; ++q) ep.contrib_out[q] = q < ep.world ? g.peers.contrib[out_parity][q] : nullptr;
   return ep;
@@ -920,36 +918,6 @@ int launch_barrier(Graph &g) {
   return MGB200_OK;
 }
 
-// MGB200_PUSH=copy: ship labels [first_label, first_label + count) of this partition's freshly written contribution
-// buffer to every peer with one peer copy each, on per-peer streams (copy engines; no SM is involved and the NVLink
-// traffic no longer shares the SMs' store path with the heavy-row gathers).  `ready` orders the copies after the kernel
-// that produced the slice; finish_peer_copies() makes the main stream wait for all of them.
-int enqueue_peer_copies(Graph &g, int parity, uint64_t first_label, uint64_t count, cudaEvent_t ready,
-                        bool used[kMaxPeers]) {
-  if (count == 0) return MGB200_OK;
-  for (uint32_t q = 0; q < g.part_world; ++q) {
-    if (q == g.part_rank) continue;
-    if (!g.copy_streams[q]) {
-      MGB_CUDA(cudaStreamCreateWithFlags(&g.copy_streams[q], cudaStreamNonBlocking));
-      MGB_CUDA(cudaEventCreateWithFlags(&g.copy_done[q], cudaEventDisableTiming));
-    }
-    MGB_CUDA(cudaStreamWaitEvent(g.copy_streams[q], ready, 0));
-    MGB_CUDA(cudaMemcpyAsync(g.peers.contrib[parity][q] + first_label, g.contrib(parity) + first_label,
-                             count * sizeof(double), cudaMemcpyDefault, g.copy_streams[q]));
-    used[q] = true;
-  }
-  return MGB200_OK;
-}
-
-int finish_peer_copies(Graph &g, const bool used[kMaxPeers]) {
-  for (uint32_t q = 0; q < g.part_world; ++q) {
-    if (!used[q]) continue;
-    MGB_CUDA(cudaEventRecord(g.copy_done[q], g.copy_streams[q]));
-    MGB_CUDA(cudaStreamWaitEvent(g.stream, g.copy_done[q], 0));
-  }
-  return MGB200_OK;
-}
-
 // One iteration.  Main stream: (iteration 1: zero-row contribution refresh) -> SELL rows -> heavy segments ->
 // heavy finish -> [join] -> iteration end.  Side stream: the SELL epilogue, forked after the SELL rows:
 // it is the kernel that pushes contributions to the peer GPUs (NVLink-bound), so it overlaps with the
@@ -960,9 +928,6 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
   const RowEpilogue ep = make_epilogue(g, it, cfg);
   const double *contrib_in = g.contrib(static_cast<int>(it & 1ull));
   uint64_t launches = 0;
-  const bool push_copy = g.tun.push_copy && g.part_world > 1 && !g.map.global_order && !g.tun.lone_partition;  // needs contiguous label ranges
-  const int out_parity = static_cast<int>((it + 1) & 1ull);
-  bool copy_used[kMaxPeers] = {};
   const bool timed = g.time_spmv && g.timed_launches < Graph::kMaxTimedLaunches;
   auto tick = [&](int cls, int edge, cudaStream_t st) -> cudaError_t {
     if (!timed) return cudaSuccess;
@@ -1040,11 +1005,6 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     row_epilogue_kernel<<<egrid, kBlockThreads, 0, es>>>(s.first_row, s.end_row, g.sell_sums, g.state, ep);
     MGB_CUDA(tick(Graph::kClsSellEpi, 1, es));
     ++launches;
-    if (push_copy && g.n_sell > 0) {  // the SELL rows' slice is final once the epilogue kernel has run
-      MGB_CUDA(cudaEventRecord(g.sell_ready_ev, es));
-      const int crc = enqueue_peer_copies(g, out_parity, g.row_lo + g.n_heavy, g.n_sell, g.sell_ready_ev, copy_used);
-      if (crc) return crc;
-    }
     if (forked) MGB_CUDA(cudaEventRecord(g.join_ev, g.stream2));
     if (spmv_count) *spmv_count += 1;
   }
@@ -1087,17 +1047,8 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
     MGB_CUDA(tick(Graph::kClsHeavyFin, 1, g.stream));
     ++launches;
     launches += 2;
-    if (push_copy && g.n_heavy > 0) {
-      MGB_CUDA(cudaEventRecord(g.heavy_ready_ev, g.stream));
-      const int crc = enqueue_peer_copies(g, out_parity, g.row_lo, g.n_heavy, g.heavy_ready_ev, copy_used);
-      if (crc) return crc;
-    }
   }
   if (forked) MGB_CUDA(cudaStreamWaitEvent(g.stream, g.join_ev, 0));
-  if (push_copy) {
-    const int crc = finish_peer_copies(g, copy_used);
-    if (crc) return crc;
-  }
   IterEndArgs e{};
   e.bar = make_barrier(g);
   e.max_iterations = cfg.max_iterations;

@@ -46,16 +46,15 @@ def run_partitioned(mg, n, f, t, world, **kw):
     return out, results, infos
 
 
-@pytest.mark.parametrize("labelling,push_mask,push", [("dealt", "0", "store"), ("global", "0", "store"),
-                                                       ("dealt", "1", "store"), ("global", "1", "store"),
-                                                       ("dealt", "0", "copy")])
+@pytest.mark.parametrize("labelling,push_mask,push_ctas", [("dealt", "1", "2"), ("dealt", "0", "2"), ("dealt", "1", "0"),
+                                                            ("global", "0", "2"), ("global", "1", "1")])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_partitioned_equals_oracle(world, labelling, push_mask, push, monkeypatch):
+def test_partitioned_equals_oracle(world, labelling, push_mask, push_ctas, monkeypatch):
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     monkeypatch.setenv("MGB200_LABELLING", labelling)  # csrc/core.hpp RowMap: contiguous dealt ranges / global order
     monkeypatch.setenv("MGB200_PUSH_MASK", push_mask)  # 1: contributions go only to the partitions that gather them
-    monkeypatch.setenv("MGB200_PUSH", push)            # copy: the exchange as peer copies on the copy engines
+    monkeypatch.setenv("MGB200_PUSH_CTAS", push_ctas)  # CTAs per SM of the push kernel next to the heavy-row kernel (0: full grid)
     import memgraph_b200 as mg
     oracle = Oracle()
     scale = 16
