@@ -110,10 +110,26 @@ def hbm_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """Per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture (or None)."""
+KERNEL_SOURCES = ("memgraph_b200/csrc/pagerank_kernels.cu", "memgraph_b200/csrc/core.hpp", "memgraph_b200/csrc/graph_build.cu")
+
+
+def kernel_source_sha():
+    import hashlib
+    h = hashlib.sha256()
+    for rel in KERNEL_SOURCES:
+        h.update(open(os.path.join(REPO, rel), "rb").read())
+    return h.hexdigest()
+
+
+def ncu_traffic(world):
+    """Per-launch DRAM bytes (read + write) of the dominant kernel from the committed `ncu --set full` capture of a
+    partition of `world` (profiles/ncu_traffic.json, written by scripts/make_ncu_traffic.py from the .ncu-rep).  The file is
+    stamped with a hash of the kernel sources it was captured from; a stale capture reads as null, not as a number."""
     try:
-        return json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))
+        d = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))
+        if d.get("kernel_source_sha256") != kernel_source_sha():
+            return None
+        return d["sell_rows_kernel_dram_bytes_per_launch"].get(str(world))
     except Exception:
         return None
 
@@ -541,10 +557,9 @@ def run_b200_arm(args):
         per_launch_bytes = ALGO_BYTES_PER_EDGE * sell_edges + ALGO_BYTES_PER_ROW * info["sell_rows"]
         avg_ms = kernel_ms / kernel_launches
         achieved = per_launch_bytes / (avg_ms * 1e-3) / 1e9
-        traffic = ncu_traffic()
         roofline = {"bound": "hbm", "kernel": "sell_rows_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "peak_source": peak_src,
-                    "traffic": (traffic or {}).get("sell_rows_kernel_dram_bytes_per_launch") if world == 1 else None,
+                    "traffic": ncu_traffic(world),
                     "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_ms,
                     "timed_launches": kernel_launches,
                     "units_per_launch": {"edges": sell_edges, "rows": info["sell_rows"]},

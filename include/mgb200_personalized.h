@@ -18,8 +18,11 @@
  *           new[v] = alpha * sum_{u->v} pr[u] / outdeg(u) + (alpha * dangling + 1 - alpha) * p[v]
  *           stop when sum_v |new[v] - pr[v]| < epsilon (converged) or after max_iterations (not converged)
  * Differences from the in-tree algorithm (mgb200_pagerank.h): dangling mass is redistributed, the stop test is the L1
- * norm, the result is not renormalised.  Edge weights: the handle's graph is unweighted (every edge counts 1, the
- * modules' default when the weight property is missing); multi-edges count with multiplicity.
+ * norm, the result is not renormalised.  Edge weights: a handle from mgb200_graph_create_host_weighted_u32() carries one
+ * non-negative FP64 weight per edge (new[v] sums w(u,v) * pr[u] / out_w[u], out_w = sum of u's out-edge weights; the
+ * modules' weight_property, default weight 1.0); on any other handle every edge counts 1.  Multi-edges count with
+ * multiplicity.  The out-weight sums are accumulated with FP64 atomics at build time: weighted results are
+ * reproducible to rounding, not bitwise; unweighted ones are bit-reproducible.
  * Single partition only.  No CPU fallback.  Tolerance-based parity (1e-9 relative vs the restatement): cuGraph's own
  * summation order is not reproducible run to run.
  */
@@ -51,6 +54,11 @@ typedef struct mgb200_cugraph_stats {
   double iterate_ms;    /* CUDA-event time of the loop */
   uint64_t kernel_launches;
 } mgb200_cugraph_stats;
+
+/* A single-partition graph handle with edge weights (dense 32-bit ids, host memory).  The in-tree PageRank and Katz on
+ * such a handle ignore the weights (their reference algorithms are unweighted). */
+int mgb200_graph_create_host_weighted_u32(int device, uint64_t n, uint64_t m, const uint32_t *from, const uint32_t *to,
+                                         const double *weight, mgb200_graph **out);
 
 /* rank_out: node_count doubles, HOST memory, original vertex-id order. */
 int mgb200_cugraph_pagerank_run(mgb200_graph *g, const mgb200_cugraph_params *params, double *rank_out,

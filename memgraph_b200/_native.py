@@ -86,6 +86,7 @@ EXPORTS = {
     "mgb200_katz_centrality": (i32, [u64, u64, vp, vp, f64, f64, u64, vp, ctypes.POINTER(u64)]),
     "mgb200_katz_tie_order": (i32, [u64, vp, vp]),
     # include/mgb200_personalized.h
+    "mgb200_graph_create_host_weighted_u32": (i32, [i32, u64, u64, vp, vp, vp, ctypes.POINTER(vp)]),
     "mgb200_cugraph_pagerank_run": (i32, [vp, ctypes.POINTER(CugraphParams), vp, ctypes.POINTER(CugraphStats)]),
     "mgb200_graph_create_rmat": (i32, [i32, u32, u64, u64, f64, f64, f64, u32, u32, ctypes.POINTER(vp)]),
     "mgb200_rmat_generate_device": (i32, [i32, u32, u64, u64, u64, f64, f64, f64, vp, vp]),

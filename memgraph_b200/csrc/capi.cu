@@ -66,15 +66,20 @@ uint64_t build_chunk_edges(uint64_t fallback) {
 
 struct DeviceArrays final : EdgeSource {  // the whole COO is resident: chunks are views
   const uint32_t *from, *to;
-  DeviceArrays(uint64_t count, const uint32_t *f, const uint32_t *t) : from(f), to(t) {
+  const double *weight;  // nullable
+  uint64_t last_first = 0;
+  DeviceArrays(uint64_t count, const uint32_t *f, const uint32_t *t, const double *w = nullptr) : from(f), to(t), weight(w) {
     m = count;
     chunk_edges = build_chunk_edges(count);
   }
   int get(uint64_t first, uint64_t, const uint32_t **f, const uint32_t **t, cudaStream_t) override {
     *f = from + first;
     *t = to + first;
+    last_first = first;
     return MGB200_OK;
   }
+  const double *weights() const override { return weight ? weight + last_first : nullptr; }
+  bool weighted() const override { return weight != nullptr; }
 };
 
 struct RmatStream final : EdgeSource {  // the synthetic workload, generated chunk by chunk: no COO is ever materialised
@@ -282,6 +287,71 @@ int mgb200_graph_create_device(int device, uint64_t n, uint64_t m, const uint32_
   h->g.part_world = part_world;
   DeviceArrays source(m, d_from, d_to);
   rc = build_graph(h->g, source);
+  if (rc) {
+    free_graph(h->g);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return MGB200_OK;
+}
+
+int mgb200_graph_create_host_weighted_u32(int device, uint64_t n, uint64_t m, const uint32_t *from, const uint32_t *to,
+                                         const double *weight, mgb200_graph **out) {
+  if (!out) return MGB200_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (m > 0 && (!from || !to || !weight)) {
+    set_error("null edge arrays");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  int rc = validate_sizes(n, 0, 1);
+  if (rc) return rc;
+  rc = check_device(device);
+  if (rc) return rc;
+  MGB_CUDA(cudaSetDevice(device));
+  for (uint64_t e = 0; e < m; ++e) {
+    if (from[e] >= n || to[e] >= n) {
+      set_error("edge endpoint out of range (>= number_of_nodes)");
+      return MGB200_ERR_INVALID_ARGUMENT;
+    }
+    if (!(weight[e] >= 0.0)) {  // cuGraph expects non-negative weights; NaN fails this test too
+      set_error("edge weights must be non-negative numbers");
+      return MGB200_ERR_INVALID_ARGUMENT;
+    }
+  }
+  uint32_t *d_from = nullptr, *d_to = nullptr;
+  double *d_w = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_from);
+    cudaFree(d_to);
+    cudaFree(d_w);
+  };
+  cudaError_t e;
+  const uint64_t cnt = std::max<uint64_t>(m, 1);
+  if ((e = cudaMalloc(&d_from, cnt * 4)) != cudaSuccess || (e = cudaMalloc(&d_to, cnt * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&d_w, cnt * 8)) != cudaSuccess ||
+      (e = cudaMemcpy(d_from, from, m * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(d_to, to, m * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(d_w, weight, m * 8, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    cleanup();
+    return cuda_fail(e, "weighted COO upload", __FILE__, __LINE__);
+  }
+  auto *h = new (std::nothrow) mgb200_graph();
+  if (!h) {
+    cleanup();
+    set_error("out of host memory");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  h->g.device = device;
+  h->g.n = n;
+  h->g.m = m;
+  h->g.part_rank = 0;
+  h->g.part_world = 1;
+  {
+    DeviceArrays source(m, d_from, d_to, d_w);
+    rc = build_graph(h->g, source);
+  }
+  cleanup();
   if (rc) {
     free_graph(h->g);
     delete h;

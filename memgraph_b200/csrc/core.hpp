@@ -174,6 +174,9 @@ struct Graph {
   uint64_t *seg_first = nullptr;  // [n_heavy + 1] first segment of each heavy row
   double *seg_partial = nullptr;  // [n_seg]
   double *heavy_sums = nullptr;   // [n_heavy] per-row gathered sums of the current iteration
+  // optional edge weights (cuGraph-semantics variants only; one partition): parallel to heavy_idx / sell_idx, pad = 0
+  double *heavy_w = nullptr, *sell_w = nullptr;
+  double *outw_l = nullptr;       // [n] sum of the out-edge weights by label (FP64 atomics: not bit-reproducible)
 
   // SELL class
   uint64_t n_slices = 0;
@@ -289,6 +292,9 @@ struct EdgeSource {
   virtual ~EdgeSource() = default;
   // device pointers to edges [first, first + count), valid until the next call (work is enqueued on `st`)
   virtual int get(uint64_t first, uint64_t count, const uint32_t **from, const uint32_t **to, cudaStream_t st) = 0;
+  // optional edge weights of the chunk last returned by get() (nullptr: unweighted graph)
+  virtual const double *weights() const { return nullptr; }
+  virtual bool weighted() const { return false; }
 };
 
 // graph_build.cu
@@ -307,7 +313,8 @@ constexpr int kSumBlocks = 1024;
 int launch_init(Graph &g, const IterateConfig &cfg);
 int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *launch_count, uint64_t *spmv_count);
 // SELL sums + heavy segment partials (heavy_row_sums: also the heavy rows' sums, into g.heavy_sums)
-int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count, bool heavy_row_sums = false);
+int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count, bool heavy_row_sums = false,
+                        bool weighted = false);  // weighted: multiply every gathered value by its edge weight
 int launch_barrier(Graph &g);
 int launch_sum_and_exchange(Graph &g);
 int launch_write_ranks_original_order(Graph &g, double *d_out);                   // single partition

@@ -89,6 +89,12 @@ __global__ void edge_key_all_kernel(uint64_t m, const uint32_t *from, const uint
     key[e] = (static_cast<uint64_t>(label_of[to[e]]) << 32) | label_of[from[e]];
 }
 
+__global__ void out_weight_kernel(uint64_t m, const uint32_t *from, const double *w, const uint32_t *label_of, double *outw_l) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t e = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < m; e += stride)
+    atomicAdd(outw_l + label_of[from[e]], w[e]);
+}
+
 __global__ void edge_key_owned_kernel(uint64_t m, const uint32_t *from, const uint32_t *to, const uint32_t *label_of,
                                       RowMap map, uint64_t row_hi, uint64_t *key,
                                       unsigned long long *cursor) {
@@ -239,7 +245,7 @@ __global__ void slice_width_kernel(uint64_t n_slices, const uint32_t *indeg_loca
 
 __global__ void sell_fill_kernel(uint64_t n_slices, uint64_t first_row, uint64_t end_row, const uint64_t *row_ptr,
                                  const uint64_t *key, const uint64_t *colbase, uint32_t pad, IndexFlags flags,
-                                 uint32_t *sell_idx) {
+                                 uint32_t *sell_idx, const double *w_sorted, double *sell_w) {
   const int lane = threadIdx.x & 31;
   const uint64_t warps_total = static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5);
   for (uint64_t s = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_slices;
@@ -256,6 +262,10 @@ __global__ void sell_fill_kernel(uint64_t n_slices, uint64_t first_row, uint64_t
     uint32_t *dst = sell_idx + c0 * kSliceRows + lane;
     for (uint32_t k = 0; k < width; ++k)
       dst[static_cast<size_t>(k) * kSliceRows] = flags(k < deg ? static_cast<uint32_t>(key[e0 + k]) : pad);
+    if (sell_w) {
+      double *wd = sell_w + c0 * kSliceRows + lane;
+      for (uint32_t k = 0; k < width; ++k) wd[static_cast<size_t>(k) * kSliceRows] = k < deg ? w_sorted[e0 + k] : 0.0;
+    }
   }
 }
 
@@ -388,6 +398,9 @@ void free_graph(Graph &g) {
   if (g.sell_sums) cudaFree(g.sell_sums);
   if (g.out_stage) cudaFree(g.out_stage);
   if (g.need_mask) cudaFree(g.need_mask);
+  if (g.heavy_w) cudaFree(g.heavy_w);
+  if (g.sell_w) cudaFree(g.sell_w);
+  if (g.outw_l) cudaFree(g.outw_l);
   void *ptrs[] = {g.label_of,  g.outdeg_l,  g.local_vertex, g.heavy_ptr,    g.heavy_idx, g.seg_row,     g.seg_begin,
                   g.seg_first, g.seg_partial, g.heavy_sums, g.sell_colbase, g.sell_idx,     g.rank,      g.window,      g.state,
                   g.sum_partials};
@@ -633,6 +646,18 @@ int build_graph(Graph &g, EdgeSource &edges) {
   uint64_t *ekey = nullptr, *ekey_alt = nullptr;
   MGB_CUDA(tmp.alloc(&ekey, g.local_edges));
   MGB_CUDA(tmp.alloc(&ekey_alt, g.local_edges));
+  const bool weighted = edges.weighted();
+  if (weighted && g.part_world > 1) {
+    set_error("edge weights are supported on a single partition only");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
+  double *eval = nullptr, *eval_alt = nullptr;  // weights travelling with the edge keys through the sort
+  if (weighted) {
+    MGB_CUDA(tmp.alloc(&eval, g.local_edges));
+    MGB_CUDA(tmp.alloc(&eval_alt, g.local_edges));
+    MGB_CUDA(keep_alloc(g, &g.outw_l, n));
+    MGB_CUDA(cudaMemsetAsync(g.outw_l, 0, n * sizeof(double), st));
+  }
   if (m && g.part_world > 1) MGB_CUDA(cudaMemsetAsync(counts + 3, 0, sizeof(unsigned long long), st));
   for (uint64_t first = 0; first < m; first += chunk_cap) {  // pass 2 over the edge list: who reads what, owned edges
     const uint64_t cnt = std::min(chunk_cap, m - first);
@@ -643,6 +668,11 @@ int build_graph(Graph &g, EdgeSource &edges) {
       need_mask_kernel<<<blocks_for(cnt, g.sm_count), kThreads, 0, st>>>(cnt, d_from, d_to, g.label_of, map, g.need_mask);
     if (g.part_world == 1) {
       edge_key_all_kernel<<<blocks_for(cnt, g.sm_count), kThreads, 0, st>>>(cnt, d_from, d_to, g.label_of, ekey + first);
+      if (weighted) {
+        const double *d_w = edges.weights();
+        MGB_CUDA(cudaMemcpyAsync(eval + first, d_w, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        out_weight_kernel<<<blocks_for(cnt, g.sm_count), kThreads, 0, st>>>(cnt, d_from, d_w, g.label_of, g.outw_l);
+      }
     } else {
       edge_key_owned_kernel<<<blocks_for(cnt, g.sm_count), kThreads, 0, st>>>(cnt, d_from, d_to, g.label_of, map, row_hi,
                                                                              ekey, counts + 3);
@@ -653,10 +683,18 @@ int build_graph(Graph &g, EdgeSource &edges) {
     cub::DoubleBuffer<uint64_t> kb(ekey, ekey_alt);
     size_t bytes = 0;
     const int end_bit = std::min(64, 32 + bits_for(g.local_rows));
-    MGB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, bytes, kb, g.local_edges, 0, end_bit, st));
     void *cub_tmp = nullptr;
-    MGB_CUDA(tmp.alloc(reinterpret_cast<char **>(&cub_tmp), bytes));
-    MGB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, bytes, kb, g.local_edges, 0, end_bit, st));
+    if (weighted) {
+      cub::DoubleBuffer<double> vb(eval, eval_alt);
+      MGB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kb, vb, g.local_edges, 0, end_bit, st));
+      MGB_CUDA(tmp.alloc(reinterpret_cast<char **>(&cub_tmp), bytes));
+      MGB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, kb, vb, g.local_edges, 0, end_bit, st));
+      eval = vb.Current();
+    } else {
+      MGB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, bytes, kb, g.local_edges, 0, end_bit, st));
+      MGB_CUDA(tmp.alloc(reinterpret_cast<char **>(&cub_tmp), bytes));
+      MGB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, bytes, kb, g.local_edges, 0, end_bit, st));
+    }
     note_mem(g);
     ekey = kb.Current();
   }
@@ -691,6 +729,10 @@ int build_graph(Graph &g, EdgeSource &edges) {
     MGB_CUDA(keep_alloc(g, &g.heavy_idx, g.heavy_edges));
     low32_kernel<<<blocks_for(g.heavy_edges, g.sm_count), kThreads, 0, st>>>(g.heavy_edges, ekey, idx_flags_heavy,
                                                                                    g.heavy_idx);
+    if (weighted) {  // rows are sorted, heavy rows first: their weights are the prefix of the sorted weights
+      MGB_CUDA(keep_alloc(g, &g.heavy_w, g.heavy_edges));
+      MGB_CUDA(cudaMemcpyAsync(g.heavy_w, eval, g.heavy_edges * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
     MGB_CUDA(keep_alloc(g, &g.seg_first, g.n_heavy + 1));
     {
       cub::TransformInputIterator<uint64_t, SegCount, const uint32_t *> it(indeg_local, SegCount{g.segment_edges});
@@ -739,9 +781,10 @@ int build_graph(Graph &g, EdgeSource &edges) {
     MGB_CUDA(cudaMemcpyAsync(g.sell_colbase + g.n_slices, &total_cols, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     g.sell_entries = total_cols * kSliceRows;
     MGB_CUDA(keep_alloc(g, &g.sell_idx, g.sell_entries));
+    if (weighted) MGB_CUDA(keep_alloc(g, &g.sell_w, g.sell_entries));
     sell_fill_kernel<<<blocks_for(g.n_slices * 32, g.sm_count), kThreads, 0, st>>>(
         g.n_slices, g.n_heavy, g.n_heavy + g.n_sell, row_ptr, ekey, g.sell_colbase, static_cast<uint32_t>(n),
-        idx_flags, g.sell_idx);
+        idx_flags, g.sell_idx, eval, g.sell_w);
     MGB_CUDA(keep_alloc(g, &g.sell_sums, g.n_sell));
     g.sell_items = env_u32("MGB200_SELL_ITEMS", static_cast<uint32_t>(g.sm_count) * 32u);
     MGB_CUDA(keep_alloc(g, &g.sell_item_begin, static_cast<uint64_t>(g.sell_items) + 1));

@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(kBlockThreads) row_epilogue_kernel(uint64_t fi
 struct SellArgs {
   const uint64_t *colbase;
   const uint32_t *idx;
+  const double *w;       // edge weights parallel to idx (weighted variants only, else nullptr)
   const WorkItem *work;  // [n_work] contiguous slice runs of ~equal cost, descending width (graph_build.cu)
   uint32_t n_work;
   WorkQueue *queue;      // ticket counter of this launch (rewound by the last CTA to leave)
@@ -418,7 +419,7 @@ constexpr int kSellUnroll = MGB_SELL_UNROLL;
 // order through a ticket counter, so a warp that drew cheap work (or sits on an SM with the longer way to L2) simply takes
 // more; the queue is software-pipelined (record of item i+1 and ticket of item i+2 in flight while item i is gathered).
 // mode 1 deals the items round-robin instead (no atomics) -- the A/B baseline of profiles/r02_sell_tickets.md.
-template <int kPath, bool kTable>
+template <int kPath, bool kTable, bool kWeighted = false>
 __device__ __forceinline__ void sell_walk(const SellArgs &a, const double *table) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = static_cast<int>(blockDim.x >> 5);
@@ -468,9 +469,21 @@ __device__ __forceinline__ void sell_walk(const SellArgs &a, const double *table
 #pragma unroll
       for (int j = 0; j < kSellUnroll; ++j)  // the next batch of indices travels while this batch is gathered
         if (k + kSellUnroll + j < ncols) nxt[j] = ld_index(p + static_cast<size_t>(k + kSellUnroll + j) * kSliceRows, pol);
+      double wv[kSellUnroll];
+      if (kWeighted) {
+        const double *pw = a.w + col_begin * kSliceRows + lane;
+#pragma unroll
+        for (int j = 0; j < kSellUnroll; ++j)
+          if (k + j < ncols) wv[j] = ld_stream_f64(pw + static_cast<size_t>(k + j) * kSliceRows, pol);
+      }
 #pragma unroll
       for (int j = 0; j < kSellUnroll; ++j)
         if (k + j < ncols) v[j] = ld_contrib_at<kPath, true, kTable>(a.contrib_in, src[j], gpol, a.window, table);
+      if (kWeighted) {
+#pragma unroll
+        for (int j = 0; j < kSellUnroll; ++j)
+          if (k + j < ncols) v[j] = __dmul_rn(wv[j], v[j]);
+      }
 #pragma unroll
       for (int j = 0; j < kSellUnroll; ++j) {
         if (k + j < ncols) {
@@ -511,6 +524,12 @@ template <int kPath>
 __global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_kernel(const SellArgs a) {
   if (ld_volatile_int(&a.state->done)) return;
   sell_walk<kPath, false>(a, nullptr);
+}
+
+// every gathered value multiplied by its edge weight (cuGraph-semantics variants, one partition)
+__global__ void __launch_bounds__(kBlockThreads, MGB_SELL_MIN_BLOCKS) sell_rows_weighted_kernel(const SellArgs a) {
+  if (ld_volatile_int(&a.state->done)) return;
+  sell_walk<kPathRange, false, true>(a, nullptr);
 }
 
 // The same walk with the hot table: ONE 1024-thread CTA per SM (the same 32 warps as 4 x 256 threads) so that the SM
@@ -557,6 +576,7 @@ __global__ void __launch_bounds__(kTableThreads, 1) sell_rows_table_kernel(const
 struct HeavyArgs {
   const uint64_t *heavy_ptr;
   const uint32_t *heavy_idx;
+  const double *heavy_w;  // edge weights parallel to heavy_idx (weighted variants only)
   const uint32_t *seg_row;
   const uint64_t *seg_begin;
   const uint64_t *seg_first;
@@ -576,7 +596,7 @@ struct HeavyArgs {
 #ifndef MGB_HEAVY_FLAGS_L2
 #define MGB_HEAVY_FLAGS_L2 1    // flagged indices: 1 = per-load L2 hot/cold selection, 0 = L1 flag only
 #endif
-template <int kPath>
+template <int kPath, bool kWeighted = false>
 __global__ void __launch_bounds__(kBlockThreads, MGB_HEAVY_MIN_BLOCKS) heavy_segments_kernel(const HeavyArgs a) {
   constexpr bool kSelL2 = MGB_HEAVY_FLAGS_L2 != 0;
   if (ld_volatile_int(&a.state->done)) return;
@@ -599,11 +619,18 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_HEAVY_MIN_BLOCKS) heavy_seg
       for (int j = 0; j < kUnroll; ++j) src[j] = ld_index(a.heavy_idx + e + 32ull * j, pol);
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib_at<kPath, kSelL2>(a.contrib_in, src[j], gpol, a.window);
+      if (kWeighted) {
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) v[j] = __dmul_rn(ld_stream_f64(a.heavy_w + e + 32ull * j, pol), v[j]);
+      }
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) acc += v[j];
     }
-    for (; e < e1; e += 32)
-      acc += ld_contrib_at<kPath, kSelL2>(a.contrib_in, ld_index(a.heavy_idx + e, pol), gpol, a.window);
+    for (; e < e1; e += 32) {
+      double v1 = ld_contrib_at<kPath, kSelL2>(a.contrib_in, ld_index(a.heavy_idx + e, pol), gpol, a.window);
+      if (kWeighted) v1 = __dmul_rn(ld_stream_f64(a.heavy_w + e, pol), v1);
+      acc += v1;
+    }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(kFull, acc, o);  // fixed tree
     if (lane == 0) a.seg_partial[g] = acc;
   }
@@ -880,7 +907,16 @@ double zero_row_rank(const Graph &g, const IterateConfig &cfg) {
 // SELL rows: the plain kernel (4 x 256 threads per SM) or, with a hot table, one 1024-thread CTA per SM
 int launch_sell_rows(Graph &g, const SellArgs &s) {
   const uint32_t table_n = s.window.table_n;
-  if (table_n > 0 && s.window.path != kPathLookup) {
+  if (s.w != nullptr) {
+    if (s.window.path != kPathRange) {
+      set_error("internal: weighted gathers exist for the single-partition range path only");
+      return MGB200_ERR_INVALID_ARGUMENT;
+    }
+    const int grid = static_cast<int>(std::min(
+        static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(sell_rows_weighted_kernel))),
+        ceil_div(g.sell_work, kWarpsPerBlock)));
+    sell_rows_weighted_kernel<<<grid, kBlockThreads, 0, g.stream>>>(s);
+  } else if (table_n > 0 && s.window.path != kPathLookup) {
     void (*const fn)(SellArgs) = s.window.path == kPathFlags ? sell_rows_table_kernel<kPathFlags> : sell_rows_table_kernel<kPathRange>;
     const int bytes = static_cast<int>(table_n * sizeof(double));
     if (g.table_attr_bytes[s.window.path == kPathFlags] < bytes) {
@@ -1077,13 +1113,18 @@ int launch_iteration(Graph &g, uint64_t it, const IterateConfig &cfg, uint64_t *
 // g.sell_sums, heavy segment partials into g.seg_partial (summed per row by the caller in segment order).  This is
 // y = A^T x for the rows of this partition with PageRank's kernels and cache policies; other SpMV-shaped paths hang
 // their own epilogue on it (Katz: omega_i = A^T omega_{i-1}, katz.cu).  Kernels return at once while state->done is set.
-int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count, bool heavy_row_sums) {
+int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count, bool heavy_row_sums, bool weighted) {
   uint64_t launches = 0;
   const GatherWindow window = make_window(g);
+  if (weighted && (window.path != kPathRange || (g.n_slices > 0 && !g.sell_w) || (g.n_seg > 0 && !g.heavy_w))) {
+    set_error("this graph handle carries no edge weights (or is partitioned)");
+    return MGB200_ERR_INVALID_ARGUMENT;
+  }
   if (g.n_slices > 0) {
     SellArgs s{};
     s.colbase = g.sell_colbase;
     s.idx = g.sell_idx;
+    s.w = weighted ? g.sell_w : nullptr;
     s.work = g.sell_work_items;
     s.n_work = g.sell_work;
     s.queue = g.queue;
@@ -1102,6 +1143,7 @@ int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count, 
     HeavyArgs h{};
     h.heavy_ptr = g.heavy_ptr;
     h.heavy_idx = g.heavy_idx;
+    h.heavy_w = weighted ? g.heavy_w : nullptr;
     h.seg_row = g.seg_row;
     h.seg_begin = g.seg_begin;
     h.seg_first = g.seg_first;
@@ -1112,7 +1154,8 @@ int launch_gather_phase(Graph &g, const double *vec_in, uint64_t *launch_count, 
     h.contrib_in = vec_in;
     h.window = window;
     h.state = g.state;
-    void (*const heavy_fn)(HeavyArgs) = window.path == kPathFlags    ? heavy_segments_kernel<kPathFlags>
+    void (*const heavy_fn)(HeavyArgs) = (weighted && g.heavy_w)          ? heavy_segments_kernel<kPathRange, true>
+                                        : window.path == kPathFlags    ? heavy_segments_kernel<kPathFlags>
                                         : window.path == kPathLookup ? heavy_segments_kernel<kPathLookup>
                                                                      : heavy_segments_kernel<kPathRange>;
     const int grid = static_cast<int>(std::min(static_cast<uint64_t>(grid_for(g, reinterpret_cast<const void *>(heavy_fn))),

@@ -46,15 +46,16 @@ __global__ void __launch_bounds__(kThreads) ppr_init_kernel(uint64_t n, double *
 
 // chunked like partial_sum_kernel: block b owns one contiguous chunk, so the partials do not depend on the grid's timing
 __global__ void __launch_bounds__(kThreads) ppr_prepare_kernel(uint64_t n, const double *pr, const uint32_t *outdeg,
-                                                               double *contrib, double *partials) {
+                                                               const double *out_weight, double *contrib, double *partials) {
   const uint64_t chunk = (n + gridDim.x - 1) / gridDim.x;
   const uint64_t lo = chunk * blockIdx.x, hi = min(lo + chunk, n);
   double dangling = 0.0;
   for (uint64_t l = lo + threadIdx.x; l < hi; l += blockDim.x) {
-    const uint32_t od = outdeg[l];
+    // out-weight sum: the weights' sum on a weighted handle, the out-degree otherwise (every edge counts 1)
+    const double ow = out_weight ? out_weight[l] : static_cast<double>(outdeg[l]);
     const double r = pr[l];
-    contrib[l] = od ? __ddiv_rn(r, static_cast<double>(od)) : 0.0;
-    if (!od) dangling += r;
+    contrib[l] = ow != 0.0 ? __ddiv_rn(r, ow) : 0.0;
+    if (ow == 0.0) dangling += r;
   }
   const double s = block_sum(dangling);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
@@ -175,10 +176,10 @@ int cugraph_pagerank_iterate(Graph &g, const mgb200_cugraph_params &prm, double 
   int converged = 0;
   double diff_host = 0.0;
   while (true) {
-    ppr_prepare_kernel<<<blocks, kThreads, 0, st>>>(n, pr, g.outdeg_l, contrib, partials);
+    ppr_prepare_kernel<<<blocks, kThreads, 0, st>>>(n, pr, g.outdeg_l, g.outw_l, contrib, partials);
     ppr_reduce_kernel<<<1, kThreads, 0, st>>>(partials, blocks, scalars);
     launches += 2;
-    int rc = launch_gather_phase(g, contrib, &launches, /*heavy_row_sums=*/true);
+    int rc = launch_gather_phase(g, contrib, &launches, /*heavy_row_sums=*/true, /*weighted=*/g.outw_l != nullptr);
     if (rc) return rc;
     PprRows rows{n, g.n_heavy, g.n_sell, g.heavy_sums, g.sell_sums, pr, p, pr_new, prm.damping_factor, scalars};
     ppr_epilogue_kernel<<<blocks, kThreads, 0, st>>>(rows, partials);

@@ -31,6 +31,23 @@ def cugraph_pagerank(graph, personalization_vertices=None, personalization_value
     return out, {f: getattr(st, f) for f, _ in N.CugraphStats._fields_}
 
 
-def cugraph_pagerank_from_edges(n, sources, targets, device=0, **kw):
-    with PageRankGraph.from_arrays(n, sources, targets, device=device) as g:
+def weighted_graph(n, sources, targets, weights, device=0):
+    """A single-partition handle with one FP64 weight per edge (mgb200_graph_create_host_weighted_u32)."""
+    f = np.ascontiguousarray(sources, dtype=np.uint32)
+    t = np.ascontiguousarray(targets, dtype=np.uint32)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    if not (len(f) == len(t) == len(w)):
+        raise ValueError("sources, targets and weights must have the same length")
+    g = PageRankGraph.__new__(PageRankGraph)
+    h = N.vp()
+    _check(N.lib().mgb200_graph_create_host_weighted_u32(device, int(n), len(f), f.ctypes.data, t.ctypes.data, w.ctypes.data,
+                                                         ctypes.byref(h)))
+    g._finish(h, device)
+    return g
+
+
+def cugraph_pagerank_from_edges(n, sources, targets, device=0, weights=None, **kw):
+    g = (PageRankGraph.from_arrays(n, sources, targets, device=device) if weights is None
+         else weighted_graph(n, sources, targets, weights, device=device))
+    with g:
         return cugraph_pagerank(g, **kw)

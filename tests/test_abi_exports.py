@@ -67,3 +67,35 @@ def test_compute_entry_points_fail_loudly_without_a_device():
         mg.pagerank_from_edges(3, [0, 1], [1, 2], number_of_threads=0)
     s, t = mg.rmat_edges_host(5, 64)  # workload synthesis is host-side and needs no device
     assert s.max() < 32 and t.max() < 32 and len(np.unique(np.stack([s, t]), axis=1).T) > 8
+
+
+def test_coo_fingerprint_is_host_only_and_order_sensitive(monkeypatch):
+    """mgb200_coo_fingerprint_u32 (the key of pagerank.so's optional device-graph cache) needs no device: equal arrays give
+    equal fingerprints, any changed / swapped / dropped edge a different one."""
+    import ctypes
+    import numpy as np
+    from memgraph_b200 import _native as N
+    lib = N.lib()
+
+    def fp(n, f, t):
+        f = np.ascontiguousarray(f, dtype=np.uint32)
+        t = np.ascontiguousarray(t, dtype=np.uint32)
+        out = (ctypes.c_uint64 * 2)()
+        assert lib.mgb200_coo_fingerprint_u32(n, len(f), f.ctypes.data, t.ctypes.data, out) == 0
+        return (out[0], out[1])
+
+    rng = np.random.default_rng(1)
+    for m in (0, 1, 1000, 600000):  # the last one crosses the multi-threaded threshold
+        f, t = rng.integers(0, 5000, m), rng.integers(0, 5000, m)
+        base = fp(5000, f, t)
+        assert fp(5000, f.copy(), t.copy()) == base
+        assert fp(5001, f, t) != base
+        if m:
+            g = f.copy(); g[m // 2] ^= 1
+            assert fp(5000, g, t) != base
+            assert fp(5000, f[:-1], t[:-1]) != base
+        if m > 1:
+            h = f.copy(); h[[0, 1]] = h[[1, 0]]
+            u = t.copy(); u[[0, 1]] = u[[1, 0]]
+            if (f[0], t[0]) != (f[1], t[1]):
+                assert fp(5000, h, u) != base  # order-sensitive: the module's dense ids follow the iteration order

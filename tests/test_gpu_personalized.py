@@ -75,3 +75,41 @@ def test_rmat_scale18_all_row_classes_and_errors():
     assert st["iterations"] == it and close(got, ref)
     ref2, it2, _ = oracle_cugraph_pagerank(n, f, t, epsilon=0.0, max_iterations=20)
     assert st2["iterations"] == it2 == 20 and close(plain, ref2)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_edge_weights(seed, monkeypatch):
+    """weight_property path: one non-negative FP64 weight per edge (mgb200_graph_create_host_weighted_u32); every gathered
+    value is multiplied by its weight, contributions are divided by the out-WEIGHT sums.  Zero weights are legal (a vertex
+    whose out-edges all weigh 0 is dangling).  Tolerance: the out-weight sums are accumulated with FP64 atomics."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(300, 4000))
+    m = int(n * rng.integers(3, 10))
+    f, t = rng.integers(0, n, m), rng.integers(0, n, m)
+    w = rng.uniform(0.0, 5.0, m)
+    w[rng.integers(0, m, m // 20)] = 0.0
+    monkeypatch.setenv("MGB200_HEAVY_MIN_DEGREE", "16")
+    for pers in [None, (rng.integers(0, n, 4), rng.uniform(0.1, 1.0, 4))]:
+        got, st = gpu(n, f, t, pers, weights=w, stop_epsilon=1e-10, max_iterations=200)
+        ref, it, conv = oracle_cugraph_pagerank(n, f, t, weights=w, personalization=pers, epsilon=1e-10, max_iterations=200)
+        assert st["iterations"] == it and bool(st["converged"]) == conv
+        assert close(got, ref)
+    # a constant weight cancels: identical to the unweighted handle up to rounding
+    a, _ = gpu(n, f, t, None, weights=np.full(m, 2.5), max_iterations=15, stop_epsilon=0.0)
+    b, _ = gpu(n, f, t, None, max_iterations=15, stop_epsilon=0.0)
+    assert float(np.max(np.abs(a - b) / b)) < 1e-12
+
+
+def test_weighted_handle_keeps_the_in_tree_algorithms_unweighted():
+    import memgraph_b200 as mg
+    from memgraph_b200 import personalized as P
+    from _checkers import Oracle
+    rng = np.random.default_rng(8)
+    n, m = 2000, 15000
+    f, t = rng.integers(0, n, m), rng.integers(0, n, m)
+    with P.weighted_graph(n, f, t, rng.uniform(0.5, 2.0, m)) as g:
+        ranks, st = g.run(max_iterations=20, stop_epsilon=0.0)
+    ref, it = Oracle().pagerank(n, f, t, max_iterations=20, stop_epsilon=0.0)
+    assert st.iterations == it and float(np.max(np.abs(ranks - ref) / ref)) < 1e-9
+    with pytest.raises(mg.MgB200Error):
+        P.weighted_graph(n, f, t, -np.ones(m))
