@@ -76,6 +76,13 @@ MGP_ABI_ENUM mgp_log_level{ /* :1805-1812 */
     MGP_LOG_LEVEL_WARN,  MGP_LOG_LEVEL_ERROR, MGP_LOG_LEVEL_CRITICAL,
 };
 
+MGP_ABI_ENUM mgp_value_type{ /* :197-217 (cugraph stand-in modules only: edge-property type test) */
+    MGP_VALUE_TYPE_NULL, MGP_VALUE_TYPE_BOOL, MGP_VALUE_TYPE_INT, MGP_VALUE_TYPE_DOUBLE, MGP_VALUE_TYPE_STRING,
+    MGP_VALUE_TYPE_LIST, MGP_VALUE_TYPE_MAP, MGP_VALUE_TYPE_VERTEX, MGP_VALUE_TYPE_EDGE, MGP_VALUE_TYPE_PATH,
+    MGP_VALUE_TYPE_DATE, MGP_VALUE_TYPE_LOCAL_TIME, MGP_VALUE_TYPE_LOCAL_DATE_TIME, MGP_VALUE_TYPE_DURATION,
+    MGP_VALUE_TYPE_ZONED_DATE_TIME, MGP_VALUE_TYPE_POINT_2D, MGP_VALUE_TYPE_POINT_3D, MGP_VALUE_TYPE_ENUM,
+};
+
 /* the procedure entry point (:1819): args, graph, result, memory live only during the call */
 typedef void (*mgp_proc_cb)(struct mgp_list *, struct mgp_graph *, struct mgp_result *, struct mgp_memory *);
 
@@ -88,6 +95,17 @@ enum mgp_error mgp_value_get_int(struct mgp_value *val, int64_t *result);       
 enum mgp_error mgp_value_get_double(struct mgp_value *val, double *result);                             /* :441 */
 enum mgp_error mgp_list_at(struct mgp_list *list, size_t index, struct mgp_value **result); /* :563 borrowed */
 enum mgp_error mgp_value_get_vertex(struct mgp_value *val, struct mgp_vertex **result);     /* :461 borrowed; gpu_bfs only */
+
+/* cugraph stand-in modules only (cugraph.pagerank.so, cugraph.personalized_pagerank.so): */
+enum mgp_error mgp_value_make_string(const char *val, struct mgp_memory *memory, struct mgp_value **result); /* :248 */
+enum mgp_error mgp_value_get_type(struct mgp_value *val, enum mgp_value_type *result);                       /* :353 */
+enum mgp_error mgp_value_get_string(struct mgp_value *val, const char **result);               /* :446 borrowed */
+enum mgp_error mgp_value_get_list(struct mgp_value *val, struct mgp_list **result);            /* :451 borrowed */
+enum mgp_error mgp_list_size(struct mgp_list *list, size_t *result);                                         /* :554 */
+enum mgp_error mgp_edge_get_property(struct mgp_edge *e, const char *property_name, struct mgp_memory *memory,
+                                     struct mgp_value **result); /* :967 new value, Null when absent */
+enum mgp_error mgp_type_string(struct mgp_type **result);                                                    /* :1692 */
+enum mgp_error mgp_type_list(struct mgp_type *element_type, struct mgp_type **result);                       /* :1741 */
 
 /* ---- result rows ---- */
 enum mgp_error mgp_result_set_error_msg(struct mgp_result *res, const char *error_msg);                 /* :716 */

@@ -113,6 +113,25 @@ def build_katz_module(objs, verbose=False):
         _run([NVCC, "-shared", "-cudart", "static", "-o", KATZ_MODULE_LIB, obj] + objs)
 
 
+CUGRAPH_MODULE_LIBS = {0: os.path.join(OUT, "cugraph.pagerank.so"), 1: os.path.join(OUT, "cugraph.personalized_pagerank.so")}
+
+
+def build_cugraph_modules(objs, verbose=False):
+    """cugraph.pagerank.so / cugraph.personalized_pagerank.so: stand-ins for the reference's cuGraph PageRank modules
+    (one source, compiled twice; module name = file stem, so the procedures are cugraph.pagerank.get and
+    cugraph.personalized_pagerank.get)."""
+    src = os.path.join(CSRC, "cugraph_modules.cpp")
+    for personalized, lib in CUGRAPH_MODULE_LIBS.items():
+        obj = os.path.join(OUT, f"cugraph_module_{personalized}.o")
+        if _newer(obj, [src] + HEADERS):
+            if verbose:
+                print(f"g++ cugraph_modules.cpp (personalized={personalized})", flush=True)
+            _run([CXX, "-std=c++20", "-O2", "-fPIC", "-fvisibility=hidden", f"-DMGB200_CUGRAPH_PERSONALIZED={personalized}",
+                  "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj])
+        if _newer(lib, objs + [obj]):
+            _run([NVCC, "-shared", "-cudart", "static", "-o", lib, obj] + objs)
+
+
 def build_fake_host(verbose=False):
     src = os.path.join(CSRC, "mgp_fake_host.cpp")
     if _newer(FAKE_HOST_LIB, [src] + HEADERS):
@@ -130,6 +149,10 @@ def build_all(verbose=False):
     if os.path.exists(os.path.join(CSRC, "gpu_bfs_module.cpp")):
         build_bfs_module(objs, verbose)
     out = {"core": CORE_LIB}
+    if os.path.exists(os.path.join(CSRC, "cugraph_modules.cpp")):
+        build_cugraph_modules(objs, verbose)
+        out["cugraph_pagerank_module"] = CUGRAPH_MODULE_LIBS[0]
+        out["cugraph_personalized_pagerank_module"] = CUGRAPH_MODULE_LIBS[1]
     if os.path.exists(os.path.join(CSRC, "katz_centrality_module.cpp")):
         build_katz_module(objs, verbose)
         out["katz_module"] = KATZ_MODULE_LIB

@@ -25,6 +25,7 @@
 #include <cctype>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <memory>
 #include <new>
@@ -45,6 +46,9 @@ struct mgp_memory {
 struct FakeGraphData {
   std::vector<int64_t> gids;                 // ascending, like Vertices(view) over in-memory storage
   std::vector<std::vector<uint32_t>> out;    // out[v] = indices of destination vertices, insertion order
+  std::vector<std::vector<double>> out_prop; // optional: one numeric edge property per out-edge (NaN = property absent)
+  std::string prop_name;                     // its name (fh_graph_set_edge_property)
+  bool prop_as_int = false;                  // hand the property out as an INTEGER value (modules must convert)
   std::unordered_map<int64_t, uint32_t> index_of;
   std::vector<char> hidden;                  // hidden[v] != 0: FindVertex fails at emission (vertex vanished mid-call, analytical mode)
   uint64_t edge_count = 0;
@@ -66,16 +70,20 @@ struct mgp_vertex {
 struct mgp_edge {
   mgp_vertex from;
   mgp_vertex to;
+  double prop = std::numeric_limits<double>::quiet_NaN();  // the edge's numeric property, NaN = absent
 };
 
-enum class ValueKind { Null, Int, Double, Vertex };
+enum class ValueKind { Null, Int, Double, Vertex, String, List };
 
+struct mgp_list;
 struct mgp_value {
   ValueKind kind = ValueKind::Null;
   int64_t i = 0;
   double d = 0.0;
   mgp_vertex *vertex = nullptr;  // owned when kind == Vertex
   bool counted = false;          // allocated through the module-facing API
+  std::string s;                         // kind == String
+  std::shared_ptr<mgp_list> list;        // kind == List
 };
 
 struct mgp_list {
@@ -83,8 +91,9 @@ struct mgp_list {
 };
 
 struct mgp_type {
-  const char *name;
+  std::string name;
   ValueKind kind;
+  const mgp_type *element = nullptr;  // kind == List
 };
 
 struct mgp_vertices_iterator {
@@ -136,6 +145,10 @@ namespace {
 mgp_type g_type_int{"INTEGER", ValueKind::Int};
 mgp_type g_type_float{"FLOAT", ValueKind::Double};
 mgp_type g_type_node{"NODE", ValueKind::Vertex};
+mgp_type g_type_string{"STRING", ValueKind::String};
+mgp_type g_type_list_node{"LIST OF NODE", ValueKind::List, &g_type_node};
+mgp_type g_type_list_float{"LIST OF FLOAT", ValueKind::List, &g_type_float};
+mgp_type g_type_list_int{"LIST OF INTEGER", ValueKind::List, &g_type_int};
 
 bool ValidIdentifier(const char *s) {  // [_[:alpha:]][_[:alnum:]]*  (mg_procedure_impl.cpp:4832-4843)
   if (!s || !*s) return false;
@@ -209,6 +222,61 @@ mgp_error mgp_list_at(mgp_list *list, size_t index, mgp_value **result) {  // :1
   return OK;
 }
 
+mgp_error mgp_list_size(mgp_list *list, size_t *result) {  // mg_procedure.h:554
+  *result = list->items.size();
+  return OK;
+}
+mgp_error mgp_value_get_list(mgp_value *val, mgp_list **result) {  // :451, unchecked in the real host
+  *result = val->list.get();
+  return OK;
+}
+mgp_error mgp_value_get_string(mgp_value *val, const char **result) {  // :446
+  *result = val->s.c_str();
+  return OK;
+}
+mgp_error mgp_value_make_string(const char *v, mgp_memory *memory, mgp_value **result) {  // :248 copies the string
+  if (memory) memory->allocations++;
+  auto *x = new (std::nothrow) mgp_value();
+  if (!x) return mgp_error::MGP_ERROR_UNABLE_TO_ALLOCATE;
+  x->kind = ValueKind::String;
+  x->s = v ? v : "";
+  x->counted = true;
+  g_live_objects++;
+  *result = x;
+  return OK;
+}
+mgp_error mgp_value_get_type(mgp_value *val, mgp_value_type *result) {  // :353
+  switch (val->kind) {
+    case ValueKind::Null: *result = mgp_value_type::MGP_VALUE_TYPE_NULL; break;
+    case ValueKind::Int: *result = mgp_value_type::MGP_VALUE_TYPE_INT; break;
+    case ValueKind::Double: *result = mgp_value_type::MGP_VALUE_TYPE_DOUBLE; break;
+    case ValueKind::Vertex: *result = mgp_value_type::MGP_VALUE_TYPE_VERTEX; break;
+    case ValueKind::String: *result = mgp_value_type::MGP_VALUE_TYPE_STRING; break;
+    case ValueKind::List: *result = mgp_value_type::MGP_VALUE_TYPE_LIST; break;
+  }
+  return OK;
+}
+// :967 -- a NEW value the caller destroys: the property, or Null when the edge does not have it
+mgp_error mgp_edge_get_property(mgp_edge *e, const char *property_name, mgp_memory *memory, mgp_value **result) {
+  if (memory) memory->allocations++;
+  auto *x = new (std::nothrow) mgp_value();
+  if (!x) return mgp_error::MGP_ERROR_UNABLE_TO_ALLOCATE;
+  const FakeGraphData *d = e->from.graph->data;
+  if (property_name && d->prop_name == property_name && e->prop == e->prop) {
+    if (d->prop_as_int) {
+      x->kind = ValueKind::Int;
+      x->i = static_cast<int64_t>(e->prop);
+    } else {
+      x->kind = ValueKind::Double;
+      x->d = e->prop;
+    }
+  }
+  x->counted = true;
+  g_live_objects++;
+  *result = x;
+  return OK;
+}
+
 // result rows (:2165-2216)
 mgp_error mgp_result_set_error_msg(mgp_result *res, const char *msg) {
   res->has_error = true;
@@ -263,7 +331,10 @@ mgp_error mgp_vertex_iter_out_edges(mgp_vertex *v, mgp_memory *memory, mgp_edges
   it->source = v->index;
   it->snapshot = v->graph->data->out[v->index];
   it->pos = 0;
-  if (!it->snapshot.empty()) it->current = mgp_edge{{it->graph, it->source, false}, {it->graph, it->snapshot[0], false}};
+  if (!it->snapshot.empty()) {
+    it->current = mgp_edge{{it->graph, it->source, false}, {it->graph, it->snapshot[0], false}};
+    if (!v->graph->data->out_prop.empty()) it->current.prop = v->graph->data->out_prop[it->source][0];
+  }
   g_live_objects++;
   *result = it;
   return OK;
@@ -281,6 +352,7 @@ mgp_error mgp_edges_iterator_next(mgp_edges_iterator *it, mgp_edge **result) {
   if (it->pos < it->snapshot.size()) it->pos++;
   if (it->pos < it->snapshot.size()) {
     it->current = mgp_edge{{it->graph, it->source, false}, {it->graph, it->snapshot[it->pos], false}};
+    if (!it->graph->data->out_prop.empty()) it->current.prop = it->graph->data->out_prop[it->source][it->pos];
     *result = &it->current;
   } else {
     *result = nullptr;
@@ -358,6 +430,17 @@ mgp_error mgp_type_node(mgp_type **result) {
   *result = &g_type_node;
   return OK;
 }
+mgp_error mgp_type_string(mgp_type **result) {  // :1692
+  *result = &g_type_string;
+  return OK;
+}
+mgp_error mgp_type_list(mgp_type *element, mgp_type **result) {  // :1741 (the three element types the modules here use)
+  if (element == &g_type_node) *result = &g_type_list_node;
+  else if (element == &g_type_float) *result = &g_type_list_float;
+  else if (element == &g_type_int) *result = &g_type_list_int;
+  else return mgp_error::MGP_ERROR_NOT_YET_IMPLEMENTED;
+  return OK;
+}
 mgp_error mgp_module_add_read_procedure(mgp_module *module, const char *name, mgp_proc_cb cb, mgp_proc **result) {
   if (!ValidIdentifier(name)) return mgp_error::MGP_ERROR_INVALID_ARGUMENT;
   if (module->procs.count(name)) return mgp_error::MGP_ERROR_LOGIC_ERROR;
@@ -392,6 +475,7 @@ mgp_error mgp_proc_add_opt_arg(mgp_proc *proc, const char *name, mgp_type *type,
   a.default_value.kind = default_value->kind;  // copied; the caller still destroys its value
   a.default_value.i = default_value->i;
   a.default_value.d = default_value->d;
+  a.default_value.s = default_value->s;
   proc->opt_args.push_back(a);
   return OK;
 }
@@ -444,6 +528,19 @@ void *fh_graph_create(uint64_t n, const int64_t *gids, uint64_t m, const int64_t
   d->edge_count = m;
   d->transactional = transactional;
   return d;
+}
+// One numeric property on the edges, in the order the edges were given to fh_graph_create (NaN = the edge lacks it).
+int fh_graph_set_edge_property(void *graph, const char *name, uint64_t m, const int64_t *src_gid, const double *values,
+                               int as_int) {
+  auto *d = static_cast<FakeGraphData *>(graph);
+  if (m != d->edge_count) return 1;
+  d->prop_name = name;
+  d->prop_as_int = as_int != 0;
+  d->out_prop.assign(d->out.size(), {});
+  for (uint64_t e = 0; e < m; ++e) d->out_prop[d->index_of.at(src_gid[e])].push_back(values[e]);  // same insertion order as `out`
+  for (size_t v = 0; v < d->out.size(); ++v)
+    if (d->out_prop[v].size() != d->out[v].size()) return 1;
+  return 0;
 }
 void fh_graph_destroy(void *graph) { delete static_cast<FakeGraphData *>(graph); }
 void fh_graph_set_abort(void *graph, int flag) { static_cast<FakeGraphData *>(graph)->abort_flag = flag; }
@@ -514,6 +611,10 @@ int fh_module_signature(void *module, const char *proc_name, char *buf, size_t c
       continue;
     }
     char num[64];
+    if (a.default_value.kind == ValueKind::String) {
+      s += a.name + " = \"" + a.default_value.s + "\" :: " + a.type->name;
+      continue;
+    }
     if (a.default_value.kind == ValueKind::Int)
       snprintf(num, sizeof(num), "%lld", static_cast<long long>(a.default_value.i));
     else
@@ -537,8 +638,11 @@ int fh_module_signature(void *module, const char *proc_name, char *buf, size_t c
 
 // CallCustomProcedure (operator.cpp:7703-7800) + argument validation (module.cpp:1584-1601,
 // module.hpp:169-202).  kinds[i] is 'i' (integer literal) or 'd' (float literal).
-void *fh_call(void *module, const char *proc_name, void *graph_data, int n_args, const char *kinds,
-              const int64_t *ivals, const double *dvals) {
+// kinds: 'i' INTEGER, 'd' FLOAT, 'v' NODE (gid in ivals), 's' STRING (svals[i]), 'V' LIST OF NODE, 'D' LIST OF FLOAT;
+// a list argument i takes list_len[i] consecutive entries of list_ivals (gids) / list_dvals, in argument order.
+void *fh_call_ex(void *module, const char *proc_name, void *graph_data, int n_args, const char *kinds,
+                 const int64_t *ivals, const double *dvals, const char *const *svals, const uint64_t *list_len,
+                 const int64_t *list_ivals, const double *list_dvals) {
   auto *m = static_cast<FhModule *>(module);
   auto *res_out = new FhResult();
   auto it = m->registry.procs.find(proc_name);
@@ -557,12 +661,17 @@ void *fh_call(void *module, const char *proc_name, void *graph_data, int n_args,
   }
   mgp_graph graph{static_cast<FakeGraphData *>(graph_data)};
   std::vector<std::unique_ptr<mgp_vertex>> arg_vertices;
+  uint64_t list_cursor = 0;
   mgp_list args;
   for (size_t i = 0; i < proc.opt_args.size(); ++i) {
     mgp_value v;
     if (i < static_cast<size_t>(n_args)) {
-      const ValueKind given = kinds[i] == 'i' ? ValueKind::Int : (kinds[i] == 'v' ? ValueKind::Vertex : ValueKind::Double);
-      if (given != proc.opt_args[i].type->kind) {  // strict: an integer literal does not satisfy FLOAT
+      const char k = kinds[i];
+      const ValueKind given = k == 'i' ? ValueKind::Int : k == 'v' ? ValueKind::Vertex : k == 's' ? ValueKind::String
+                              : (k == 'V' || k == 'D') ? ValueKind::List : ValueKind::Double;
+      const mgp_type *want = proc.opt_args[i].type;
+      const bool element_ok = given != ValueKind::List || (want->element && want->element->kind == (k == 'V' ? ValueKind::Vertex : ValueKind::Double));
+      if (given != want->kind || !element_ok) {  // strict: an integer literal does not satisfy FLOAT
         res_out->error = "'" + fq + "' argument named '" + proc.opt_args[i].name + "' at position " +
                          std::to_string(i) + " must be of type " + proc.opt_args[i].type->name + ".";
         return res_out;
@@ -570,6 +679,27 @@ void *fh_call(void *module, const char *proc_name, void *graph_data, int n_args,
       v.kind = given;
       v.i = ivals[i];
       v.d = dvals[i];
+      if (given == ValueKind::String) v.s = (svals && svals[i]) ? svals[i] : "";
+      if (given == ValueKind::List) {
+        v.list = std::make_shared<mgp_list>();
+        for (uint64_t j = 0; j < (list_len ? list_len[i] : 0); ++j, ++list_cursor) {
+          mgp_value item;
+          if (k == 'V') {
+            auto found = graph.data->index_of.find(list_ivals[list_cursor]);
+            if (found == graph.data->index_of.end()) {
+              res_out->error = "'" + fq + "': no vertex with the given id";
+              return res_out;
+            }
+            arg_vertices.push_back(std::make_unique<mgp_vertex>(mgp_vertex{&graph, found->second, false}));
+            item.kind = ValueKind::Vertex;
+            item.vertex = arg_vertices.back().get();
+          } else {
+            item.kind = ValueKind::Double;
+            item.d = list_dvals[list_cursor];
+          }
+          v.list->items.push_back(item);
+        }
+      }
       if (given == ValueKind::Vertex) {  // a NODE argument is passed by gid
         auto found = graph.data->index_of.find(ivals[i]);
         if (found == graph.data->index_of.end()) {
@@ -597,7 +727,7 @@ void *fh_call(void *module, const char *proc_name, void *graph_data, int n_args,
     double rank = 0.0;
     for (size_t f = 0; f < proc.results.size(); ++f) {
       if (proc.results[f].first == "node") node = row->fields[f].i;
-      if (proc.results[f].first == "rank") rank = row->fields[f].d;
+      if (proc.results[f].first == "rank" || proc.results[f].first == "pagerank") rank = row->fields[f].d;
       if (proc.results[f].first == "distance") rank = static_cast<double>(row->fields[f].i);  // INTEGER result column
     }
     res_out->nodes.push_back(node);
@@ -605,6 +735,11 @@ void *fh_call(void *module, const char *proc_name, void *graph_data, int n_args,
   }
   return res_out;
 }
+void *fh_call(void *module, const char *proc_name, void *graph_data, int n_args, const char *kinds,
+              const int64_t *ivals, const double *dvals) {
+  return fh_call_ex(module, proc_name, graph_data, n_args, kinds, ivals, dvals, nullptr, nullptr, nullptr, nullptr);
+}
+
 const char *fh_result_error(void *result) {
   auto *r = static_cast<FhResult *>(result);
   return r->error.empty() ? nullptr : r->error.c_str();

@@ -36,6 +36,10 @@ def host():
         H.fh_module_signature.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
         H.fh_call.restype = vp
         H.fh_call.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p]
+        H.fh_call_ex.restype = vp
+        H.fh_call_ex.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p,
+                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        H.fh_graph_set_edge_property.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint64, i64p, f64p, ctypes.c_int]
         H.fh_result_error.restype = ctypes.c_char_p
         H.fh_result_error.argtypes = [vp]
         H.fh_result_rows.restype = ctypes.c_uint64
@@ -47,6 +51,8 @@ def host():
 
 
 BFS_MODULE_SO = os.path.join(REPO, "memgraph_b200", "_build", "gpu_bfs.so")
+CUGRAPH_PAGERANK_SO = os.path.join(REPO, "memgraph_b200", "_build", "cugraph.pagerank.so")
+CUGRAPH_PERSONALIZED_SO = os.path.join(REPO, "memgraph_b200", "_build", "cugraph.personalized_pagerank.so")
 
 
 class Node:
@@ -69,6 +75,13 @@ class Graph:
                                         1 if transactional else 0)
         if not self.h:
             raise ValueError("edge endpoint is not a vertex of the graph")
+
+    def set_edge_property(self, name, src_gid, values, as_int=False):
+        """One numeric property on the edges, in the order they were given to the constructor (NaN = edge lacks it)."""
+        s = np.ascontiguousarray(src_gid, dtype=np.int64)
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        if host().fh_graph_set_edge_property(self.h, name.encode(), len(v), s.ctypes.data, v.ctypes.data, 1 if as_int else 0):
+            raise ValueError("edge property does not match the graph's edges")
 
     def set_abort(self, flag=True):
         host().fh_graph_set_abort(self.h, 1 if flag else 0)
@@ -109,12 +122,40 @@ class Module:
     def call(self, graph, *args, proc="get"):
         """args: Python ints are INTEGER literals, floats are FLOAT literals (strictly typed).
         Returns (node_gids, ranks) in emission order."""
-        kinds = "".join("v" if isinstance(a, Node) else
-                        ("i" if isinstance(a, (int, np.integer)) and not isinstance(a, bool) else "d") for a in args)
+        def kind(a):
+            if isinstance(a, Node):
+                return "v"
+            if isinstance(a, str):
+                return "s"
+            if isinstance(a, (list, tuple)):  # LIST OF NODE / LIST OF FLOAT (an empty list is typed by the signature slot)
+                return "V" if (a and isinstance(a[0], Node)) else "D"
+            return "i" if isinstance(a, (int, np.integer)) and not isinstance(a, bool) else "d"
+
+        kinds = "".join(kind(a) for a in args)
+        if "D" in kinds:  # an empty Python list carries no element type: take it from the procedure's signature
+            sig = self.signature(proc)
+            slots = sig[sig.index("(") + 1:sig.index(") ::")].split(", ")
+            kinds = "".join("V" if (k == "D" and not a and "LIST OF NODE" in slots[i]) else k
+                            for i, (k, a) in enumerate(zip(kinds, args)))
         iv = np.array([a.gid if k == "v" else (int(a) if k == "i" else 0) for a, k in zip(args, kinds)] + [0],
                       dtype=np.int64)
         dv = np.array([float(a) if k == "d" else 0.0 for a, k in zip(args, kinds)] + [0.0], dtype=np.float64)
-        r = host().fh_call(self.h, proc.encode(), graph.h, len(args), kinds.encode(), iv.ctypes.data, dv.ctypes.data)
+        sv = (ctypes.c_char_p * (len(args) + 1))(*[a.encode() if k == "s" else None for a, k in zip(args, kinds)], None)
+        ll = np.array([len(a) if k in "VD" else 0 for a, k in zip(args, kinds)] + [0], dtype=np.uint64)
+        li = np.array([x.gid for a, k in zip(args, kinds) if k == "V" for x in a] + [0], dtype=np.int64)
+        ld = np.array([float(x) for a, k in zip(args, kinds) if k == "D" for x in a] + [0.0], dtype=np.float64)
+        # fh_call_ex walks list_ivals / list_dvals with ONE cursor over all list arguments in order: interleave accordingly
+        if "V" in kinds and "D" in kinds:
+            li_full, ld_full = [], []
+            for a, k in zip(args, kinds):
+                if k == "V":
+                    li_full += [x.gid for x in a]; ld_full += [0.0] * len(a)
+                elif k == "D":
+                    li_full += [0] * len(a); ld_full += [float(x) for x in a]
+            li = np.array(li_full + [0], dtype=np.int64)
+            ld = np.array(ld_full + [0.0], dtype=np.float64)
+        r = host().fh_call_ex(self.h, proc.encode(), graph.h, len(args), kinds.encode(), iv.ctypes.data, dv.ctypes.data,
+                              sv, ll.ctypes.data, li.ctypes.data, ld.ctypes.data)
         try:
             err = host().fh_result_error(r)
             if err is not None:
