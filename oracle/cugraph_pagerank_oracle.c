@@ -9,7 +9,7 @@
  * (cpp/src/link_analysis/pagerank_impl.cuh), restated here:
  *     pr_0 = 1/N;  p = personalization values / their sum on the given vertices, 0 elsewhere  (absent: p = 1/N)
  *     out_w[u] = sum of the weights of u's out-edges (weight 1 when the graph is unweighted)
- *     repeat:  dangling = sum_{u: out_w[u] == 0} pr[u]
+ *     repeat:  dangling = sum_{u: out_w[u] == 0} pr[u]      (such a u contributes nothing along its zero-weight edges)
  *              new[v]   = alpha * sum_{(u->v)} w(u,v) * pr[u] / out_w[u]  +  (alpha * dangling + 1 - alpha) * p[v]
  *              diff     = sum_v |new[v] - pr[v]|;  pr = new;  ++iterations
  *              stop if diff < epsilon (converged) or iterations >= max_iterations (not converged)
@@ -68,7 +68,9 @@ int oracle_cugraph_pagerank(uint64_t n, uint64_t m, const uint64_t *from, const 
       if (out_w[v] == 0.0) dangling += pr[v];
     const double spread = alpha * dangling + (1.0 - alpha);
     for (uint64_t v = 0; v < n; ++v) nw[v] = 0.0;
-    for (uint64_t e = 0; e < m; ++e) nw[to[e]] += (weight ? weight[e] : 1.0) * (pr[from[e]] / out_w[from[e]]);
+    /* a vertex whose out-edges all weigh 0 is dangling: its mass went into `dangling`, its edges carry nothing */
+    for (uint64_t e = 0; e < m; ++e)
+      if (out_w[from[e]] != 0.0) nw[to[e]] += (weight ? weight[e] : 1.0) * (pr[from[e]] / out_w[from[e]]);
     double diff = 0.0;
     for (uint64_t v = 0; v < n; ++v) {
       nw[v] = alpha * nw[v] + spread * p[v];
