@@ -218,6 +218,10 @@ struct Graph {
   cudaEvent_t join_ev = nullptr;
   bool overlap_epilogue = true;
   bool stream_attr_set = false;
+  static constexpr int kOccSlots = 24;  // occupancy of every kernel launched on this handle, asked once (grid_for)
+  mutable const void *occ_kernel[kOccSlots] = {};
+  mutable int occ_blocks[kOccSlots] = {};
+  mutable int occ_cached = 0;
   int table_attr_bytes[2] = {0, 0};  // dynamic shared memory already granted to sell_rows_table_kernel<range / flags>
   struct Tunables {  // environment, read once per graph in build_graph()
     uint64_t l2_hot_mb = 64;     // MGB200_L2_HOT_MB: evict-last window of the gathered vector (64 = effective L2, l2_bench)

@@ -593,6 +593,9 @@ struct HeavyArgs {
 #ifndef MGB_HEAVY_MIN_BLOCKS
 #define MGB_HEAVY_MIN_BLOCKS 8  // 32 registers: occupancy beats the 8-16 B of spill (measured, r01_multi_gpu.md)
 #endif
+#ifndef MGB_HEAVY_PREFETCH
+#define MGB_HEAVY_PREFETCH 0    // 1: request the next batch of segment indices before consuming the current gathers
+#endif
 #ifndef MGB_HEAVY_FLAGS_L2
 #define MGB_HEAVY_FLAGS_L2 1    // flagged indices: 1 = per-load L2 hot/cold selection, 0 = L1 flag only
 #endif
@@ -612,11 +615,28 @@ __global__ void __launch_bounds__(kBlockThreads, MGB_HEAVY_MIN_BLOCKS) heavy_seg
     const uint64_t e1 = (e0 + a.segment_edges < row_end) ? e0 + a.segment_edges : row_end;
     double acc = 0.0;
     uint64_t e = e0 + lane;
+#if MGB_HEAVY_PREFETCH
+    // software pipeline like the SELL walk: the indices of batch k+1 are requested before the gathers of batch k are consumed
+    uint32_t nxt[kUnroll];
+    if (e + 32ull * (kUnroll - 1) < e1) {
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) nxt[j] = ld_index(a.heavy_idx + e + 32ull * j, pol);
+    }
+#endif
     for (; e + 32ull * (kUnroll - 1) < e1; e += 32ull * kUnroll) {
       uint32_t src[kUnroll];
       double v[kUnroll];
+#if MGB_HEAVY_PREFETCH
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) src[j] = nxt[j];
+      if (e + 32ull * kUnroll + 32ull * (kUnroll - 1) < e1) {
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) nxt[j] = ld_index(a.heavy_idx + e + 32ull * kUnroll + 32ull * j, pol);
+      }
+#else
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) src[j] = ld_index(a.heavy_idx + e + 32ull * j, pol);
+#endif
 #pragma unroll
       for (int j = 0; j < kUnroll; ++j) v[j] = ld_contrib_at<kPath, kSelL2>(a.contrib_in, src[j], gpol, a.window);
       if (kWeighted) {
@@ -824,12 +844,19 @@ __global__ void __launch_bounds__(kBlockThreads) write_local_kernel(uint64_t loc
 
 // ---- host-side launch helpers -------------------------------------------------------------------------
 
-int grid_for(const Graph &g, const void *kernel, uint64_t work_items_per_block_hint = 0) {
+// a whole number of resident waves on the SMs; the occupancy query is made once per kernel per graph handle (it used
+// to be ~6 driver calls per iteration)
+int grid_for(const Graph &g, const void *kernel, int threads = kBlockThreads) {
+  for (int i = 0; i < g.occ_cached; ++i)
+    if (g.occ_kernel[i] == kernel) return g.sm_count * g.occ_blocks[i];
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockThreads, 0) != cudaSuccess || per_sm < 1)
-    per_sm = 4;
-  (void)work_items_per_block_hint;
-  return g.sm_count * per_sm;  // a whole number of resident waves on 148 SMs
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+  if (g.occ_cached < Graph::kOccSlots) {
+    g.occ_kernel[g.occ_cached] = kernel;
+    g.occ_blocks[g.occ_cached] = per_sm;
+    ++g.occ_cached;
+  }
+  return g.sm_count * per_sm;
 }
 
 uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }

@@ -10,9 +10,10 @@ sys.path.insert(0, REPO)
 from memgraph_b200 import build as B  # noqa: E402
 
 VARIANTS = {
-    "s_u8b4": [], "s_u4b6": ["-DMGB_SELL_UNROLL=4", "-DMGB_SELL_MIN_BLOCKS=6"],
-    "s_u6b5": ["-DMGB_SELL_UNROLL=6", "-DMGB_SELL_MIN_BLOCKS=5"], "s_u4b8": ["-DMGB_SELL_UNROLL=4", "-DMGB_SELL_MIN_BLOCKS=8"],
-    "s_u8b5": ["-DMGB_SELL_MIN_BLOCKS=5"],
+    "h_base": [], "h_pf8": ["-DMGB_HEAVY_PREFETCH=1"], "h_pf6": ["-DMGB_HEAVY_PREFETCH=1", "-DMGB_HEAVY_MIN_BLOCKS=6"],
+    "h_pf5": ["-DMGB_HEAVY_PREFETCH=1", "-DMGB_HEAVY_MIN_BLOCKS=5"], "h_pf4": ["-DMGB_HEAVY_PREFETCH=1", "-DMGB_HEAVY_MIN_BLOCKS=4"],
+    "h_b6": ["-DMGB_HEAVY_MIN_BLOCKS=6"], "h_b4": ["-DMGB_HEAVY_MIN_BLOCKS=4"],
+    "h_u4pf8": ["-DMGB_HEAVY_PREFETCH=1", "-DMGB_UNROLL=4"], "h_u4b8": ["-DMGB_UNROLL=4"],
 }
 
 
@@ -32,7 +33,7 @@ def main():
         sell = ""
         lines = log.stdout.splitlines()
         for i, l in enumerate(lines):
-            if "Compiling entry function" in l and "sell_rows_kernelILi0E" in l:
+            if "Compiling entry function" in l and "heavy_segments_kernelILi0ELb0E" in l:
                 sell = " | ".join(x.strip() for x in lines[i + 1:i + 4])
         subprocess.run([B.NVCC, "-shared", "-cudart", "static", "-o", os.path.join(out, "libmgb200_pagerank.so"), obj] + others, check=True)
         print(f"{name:10s} {sell}")
