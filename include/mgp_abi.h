@@ -5,7 +5,7 @@
  * include/mg_procedure.h (2170 lines; memgraph/memgraph @ 292f896a).  Every prototype below names
  * the line of that header it restates, so a maintainer can diff them; the module also compiles
  * against the reference header itself (-DMGB200_USE_REFERENCE_MGP_HEADER -I<reference>/include,
- * exercised by tests/test_abi_contract.py where the checkout exists), which proves the two agree
+ * exercised by tests/test_module_host.py::test_module_compiles_against_the_reference_header where the checkout exists), which proves the two agree
  * on every call the module makes.
  *
  * Exports the module must provide (mg_procedure.h:1780-1793, loader: src/query/procedure/module.cpp:868-929):
