@@ -132,8 +132,11 @@ def build_cugraph_modules(objs, verbose=False):
             _run([NVCC, "-shared", "-cudart", "static", "-o", lib, obj] + objs)
 
 
+FAKE_HOST_SRC = os.path.join(REPO, "tests", "mgp_fake_host.cpp")  # test infrastructure: lives with the tests
+
+
 def build_fake_host(verbose=False):
-    src = os.path.join(CSRC, "mgp_fake_host.cpp")
+    src = FAKE_HOST_SRC
     if _newer(FAKE_HOST_LIB, [src] + HEADERS):
         if verbose:
             print("g++ mgp_fake_host.cpp", flush=True)
@@ -144,7 +147,7 @@ def build_all(verbose=False):
     objs = build_core(verbose)
     if os.path.exists(os.path.join(CSRC, "pagerank_module.cpp")):
         build_module(objs, verbose)
-    if os.path.exists(os.path.join(CSRC, "mgp_fake_host.cpp")):
+    if os.path.exists(FAKE_HOST_SRC):
         build_fake_host(verbose)
     if os.path.exists(os.path.join(CSRC, "gpu_bfs_module.cpp")):
         build_bfs_module(objs, verbose)
@@ -160,7 +163,7 @@ def build_all(verbose=False):
         out["bfs_module"] = BFS_MODULE_LIB
     if os.path.exists(os.path.join(CSRC, "pagerank_module.cpp")):
         out["module"] = MODULE_LIB
-    if os.path.exists(os.path.join(CSRC, "mgp_fake_host.cpp")):
+    if os.path.exists(FAKE_HOST_SRC):
         out["fake_host"] = FAKE_HOST_LIB
     return out
 

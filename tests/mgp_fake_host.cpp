@@ -1,4 +1,4 @@
-// memgraph_b200/csrc/mgp_fake_host.cpp -- a minimal in-memory HOST for Memgraph query modules.
+// tests/mgp_fake_host.cpp -- a minimal in-memory HOST for Memgraph query modules.
 //
 // TEST INFRASTRUCTURE.  The real host (memgraph: src/query/procedure/mg_procedure_impl.cpp, module.cpp,
 // src/query/plan/operator.cpp) cannot be built here (35 conan packages, no network), so this file plays
