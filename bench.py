@@ -506,7 +506,10 @@ def run_b200_arm(args):
     # reference's EdgePair and uint32 dense ids as the module holds them; (b) the drop-in module through the mgp ABI
     # (tests' fake host; ABI-bound: 3 calls per edge, 5 per emitted row) on a smaller graph.
     e2e_call = None
-    if world == 1 and not args.no_e2e_call and lone <= 1:
+    host_gib = os.sysconf("SC_PHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2**30
+    if world == 1 and not args.no_e2e_call and lone <= 1 and host_gib < 40 * m / 2**30 + 16:
+        log(f"e2e_call skipped: {host_gib:.0f} GiB of host memory is not enough for the host COO copies of scale-{scale}")
+    elif world == 1 and not args.no_e2e_call and lone <= 1:
         try:
             e2e_call = measure_e2e_call(args, mg, N, lib, device, scale, n, m, host_out)
         except Exception as ex:  # pragma: no cover
