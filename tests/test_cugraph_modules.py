@@ -113,3 +113,20 @@ def test_weight_property_isolated_vertices_and_seeds():
             ref5, _, _ = oracle_cugraph_pagerank(len(used), f, t, weights=wi, epsilon=1e-10)
             assert float(np.max(np.abs(ranks5 - ref5) / ref5)) < 1e-9
     assert fh.host().fh_live_objects() == 0
+
+
+@needs_modules
+@pytest.mark.parametrize("path", [fh.CUGRAPH_PAGERANK_SO, fh.CUGRAPH_PERSONALIZED_SO, fh.BFS_MODULE_SO])
+def test_modules_import_only_declared_mgp_symbols_and_no_cuda(path):
+    """Loader contract (module.cpp:861 dlopen RTLD_NOW | RTLD_LOCAL): the module exports the two entry points, every undefined
+    mgp_* symbol is one include/mgp_abi.h declares, and nothing CUDA / NCCL is left undefined (static runtime)."""
+    import re
+    import subprocess
+    defined = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    assert " T mgp_init_module" in defined and " T mgp_shutdown_module" in defined
+    und = subprocess.run(["nm", "-D", "--undefined-only", path], capture_output=True, text=True, check=True).stdout
+    imported = {line.split()[-1] for line in und.splitlines() if " mgp_" in line}
+    header = open(os.path.join(os.path.dirname(fh.REPO + "/"), "include", "mgp_abi.h")).read()
+    declared = set(re.findall(r"\b(mgp_[a-z_0-9]+)\s*\(", header))
+    assert imported <= declared, imported - declared
+    assert "cuda" not in und.lower() and "nccl" not in und.lower()
